@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: object-level multi-view fusion with semantic view selection
+(BASELINE.json configs[1]): per GPU a batch of 64 synthetic MV-TOD-shaped scenes, V=73 views of
+480x640, N=100k points, Q=21 objects, C=768, production flags of tools/preprocess_data.py:177-185.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch. `value` = scenes/s with inputs resident in
+HBM; `e2e` = the same metric through the reference-shaped call MultiviewFeatureFusion.fuse() with
+host numpy inputs (pinned staging + H2D + D2H inside the timed region). `--impl reference` times
+the CPU restatement of the reference's own torch/numpy path (oracle/fusion_ref.py; the reference is
+pure Python and /root/reference does not exist on the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOAD = "mvtod_object_fusion_sim_max_batch64_V73_N100k_Q21_C768"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenes", type=int, default=64, help="scenes per GPU per step")
+    ap.add_argument("--unique", type=int, default=8, help="distinct generated scenes per GPU (replicated to --scenes)")
+    ap.add_argument("--views", type=int, default=73)
+    ap.add_argument("--points", type=int, default=100_000)
+    ap.add_argument("--objects", type=int, default=21)
+    ap.add_argument("--e2e-scenes", type=int, default=4, help="scenes per e2e step through the host API")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = sorted(sm)[len(sm) // 2:]
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm / CPU baseline
+def cpu_scene(args, seed=1234):
+    from dropclip_b200.scenes import make_scene
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    sc = make_scene(seed, n_views=args.views, n_points=args.points, n_objects=args.objects, device=dev)
+    return sc
+
+
+def time_cpu_reference(sc, repeats=1):
+    """Seconds per scene of the reference's CPU path (oracle port, all host threads)."""
+    from oracle import fusion_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    K = fusion_ref.intrinsic_matrix(sc.intrinsic)
+    H, W = sc.intrinsic["height"], sc.intrinsic["width"]
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        fusion_ref.fuse_object_level(sc.points, sc.colors, sc.labels, sc.depths, sc.seg_masks, sc.camera_poses,
+                                     sc.mv_features, sc.query_embeddings, K, H, W, use_visibility=False,
+                                     use_similarity=True, sim_method="max", return_obj=True, device="cpu")
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sc = cpu_scene(args)
+    for _ in range(args.warmup):
+        time_cpu_reference(sc)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        time_cpu_reference(sc)
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "fused_scenes_per_sec", "value": val, "unit": "scenes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
+        "points_per_sec": val * args.points,
+        "config": {"workload": WORKLOAD, "views": args.views, "points": args.points, "objects": args.objects,
+                   "feat_dim": 768, "flags": "use_obj_prior=1,use_similarity=1,use_visibility=0,sim_kernel=max"},
+        "cpu_baseline": {"value": val, "unit": "scenes/s", "cores": cores, "kind": "port",
+                         "sample": "1 scene of the workload per step (V=%d, N=%d), oracle/fusion_ref.py" % (args.views, args.points)},
+        "e2e": {"value": val, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def algorithmic_bytes(b, mask_elem=1):
+    """SURVEY.md §8(d) per-scene figures x the scenes of one launch."""
+    HW = b.height * b.width
+    seg_elem = b.segs.element_size()
+    vis = sum(24 * n + v * n * (4 + mask_elem) for n, v in zip(b.n_points, b.n_views))
+    seg = sum(v * HW * seg_elem for v in b.n_views)
+    fe = b.feats.element_size()
+    dim = int(b.feats.shape[1])
+    wmean = b.total_rows * dim * fe + sum(q * v * 4 + q * dim * 4 for q, v in zip(b.n_queries, b.n_views))
+    score_flops = 2 * b.total_rows * dim * max(b.n_queries)
+    return {"project_visibility": vis, "seg_histogram": seg, "segmented_wmean": wmean, "view_score_flops": score_flops}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from dropclip_b200.engine import FusionEngine, batch_from_device
+    from dropclip_b200.feature_fusion import MultiviewFeatureFusion
+    from dropclip_b200.scenes import make_scene
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = FusionEngine(dev)
+    # ---- synthetic batch, generated on the device; scene ids are sharded rank::world (weak scaling)
+    uniq = []
+    for i in range(args.unique):
+        sid = 1234 + rank * args.scenes + i
+        uniq.append(make_scene(sid, n_views=args.views, n_points=args.points, n_objects=args.objects, device=str(dev),
+                               as_torch=True))
+    scenes = [uniq[i % args.unique] for i in range(args.scenes)]
+    batch = batch_from_device(scenes, dev, seg_dtype=torch.int64)  # torch.cat copies: every scene has its own memory
+    torch.cuda.synchronize()
+
+    def step():
+        res = eng.fuse_object_level(batch, 0.05, False, True, "max", torch.uint8)
+        comp = eng.compact(batch, res["any_visible"], res["mask"])
+        if world > 1:
+            gathered = torch.empty((world,) + tuple(res["fused"].shape), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(gathered, res["fused"])
+        return res, comp
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    eng.launches = 0
+    eng.profile = {}
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        res, comp = step()
+    end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([start.elapsed_time(end)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = eng.launches
+    prof = eng.profile_ms()
+    eng.profile = None
+    ms_step = ms_total / args.steps
+    scenes_per_s = world * args.scenes / (ms_step * 1e-3)
+    points_per_s = scenes_per_s * args.points
+
+    # ---- roofline of the dominant kernel (live CUDA-event durations from the timed region)
+    alg = algorithmic_bytes(batch)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
+    kernels = {}
+    for name in ("project_visibility", "seg_histogram", "segmented_wmean"):
+        if name in prof and prof[name] > 0:
+            gbs = alg[name] / (prof[name] * 1e-3) / 1e9
+            kernels[name] = {"ms": prof[name], "alg_bytes": alg[name], "gbs": gbs, "frac": gbs / hbm_peak}
+    if "view_score" in prof:
+        kernels["view_score"] = {"ms": prof["view_score"], "flops": alg["view_score_flops"],
+                                 "tflops": alg["view_score_flops"] / (prof["view_score"] * 1e-3) / 1e12}
+    top = max(("project_visibility", "seg_histogram"), key=lambda k: kernels.get(k, {}).get("ms", 0.0))
+    roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": kernels[top]["frac"], "traffic": None, "peak_source": peak_src,
+                "share_of_step": kernels[top]["ms"] / ms_step, "kernels": kernels}
+
+    # ---- end to end through the reference-shaped host API
+    e2e = None
+    if not args.no_e2e:
+        host = [make_scene(1234 + rank * args.scenes + i, n_views=args.views, n_points=args.points, n_objects=args.objects,
+                           device=str(dev)) for i in range(args.e2e_scenes)]
+        M = MultiviewFeatureFusion(host[0].intrinsic, use_visibility=0, use_similarity=1, use_sim_kernel="max",
+                                   use_obj_prior=1, norm_feat=False, device=dev)
+
+        def e2e_step():
+            outs = []
+            for s in host:
+                (f, w, vis), (p, c, l) = M.fuse(s.points, s.colors, s.labels, s.depths, s.seg_masks, s.camera_poses,
+                                                s.mv_features, s.query_embeddings, return_obj=True, device=dev)
+                outs.append((f.cpu(), w.cpu(), vis))  # device->host read of the step's results
+            return outs
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n_e2e = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            outs = e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        s0 = host[0]
+        h2d = sum(sum(d.nbytes for d in s.depths) + sum(m.nbytes for m in s.seg_masks) + s.points.nbytes + s.labels.nbytes
+                  + sum(f.numel() * f.element_size() for f in s.mv_features) + s.query_embeddings.numel() * 4
+                  + len(s.depths) * 64 for s in host)
+        d2h = sum(f.numel() * 4 + w.numel() * 4 + vis.numel() for f, w, vis in outs) + sum(s.points.shape[0] for s in host)
+        e2e = {"value": world * args.e2e_scenes * n_e2e / float(dt.item()), "unit": "scenes/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "scenes_per_step": args.e2e_scenes,
+               "api": "MultiviewFeatureFusion.fuse(host numpy inputs, return_obj=True)", "steps": n_e2e}
+        del host, M
+
+    # ---- CPU baseline (rank 0, N=1): one scene of the workload through the oracle port
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sc = cpu_scene(args)
+        sec = time_cpu_reference(sc)
+        cpu = {"value": 1.0 / sec, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "1 scene of the workload (V=%d, N=%d) through oracle/fusion_ref.fuse_object_level, %.1f s" % (
+                   args.views, args.points, sec)}
+
+    if rank == 0:
+        line = {
+            "metric": "fused_scenes_per_sec", "value": scenes_per_s, "unit": "scenes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32(f16 tensor operands)", "data": "synthetic",
+            "points_per_sec": points_per_s, "point_views_per_sec": points_per_s * args.views,
+            "config": {"workload": WORKLOAD, "scenes_per_gpu": args.scenes, "unique_scenes_per_gpu": args.unique,
+                       "views": args.views, "points": args.points, "objects": args.objects, "feat_dim": 768,
+                       "image": "480x640", "seg_dtype": "int64", "mask_dtype": "uint8", "feature_dtype": "fp16",
+                       "flags": "use_obj_prior=1,use_similarity=1,use_visibility=0,sim_kernel=max,return_obj=True",
+                       "parallelism": "scene-parallel x%d, no data-path collective; all_gather of fused features" % world,
+                       "l2": "inputs per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (batch.h2d_bytes() / 1e9)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

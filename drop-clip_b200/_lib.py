@@ -1,0 +1,101 @@
+"""ctypes binding of libdropclip.so (the C ABI declared in include/dropclip.h).
+
+There is no fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdropclip.so")
+
+DC_F16, DC_F32, DC_U8, DC_I32, DC_I64, DC_F64 = 0, 1, 2, 3, 4, 5
+DC_SIM_NONE, DC_SIM_MAX, DC_SIM_MEAN = 0, 1, 2
+DC_GROUND_RAW, DC_GROUND_PAIRED, DC_GROUND_ARGMAX = 0, 1, 2
+ABI_VERSION = 1
+
+P = c_void_p
+# name -> (restype, argtypes); must list every DC_API symbol of include/dropclip.h
+SIGNATURES = {
+    "dc_abi_version": (c_int, []),
+    "dc_last_error": (c_char_p, []),
+    "dc_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
+    "dc_project_visibility": (c_int, [P, P, P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_double, P, c_int, P, P,
+                                      c_int, P, P]),
+    "dc_seg_histogram": (c_int, [P, c_int, c_int64, c_int64, c_int, P, P, P]),
+    "dc_view_table": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, P, P, P, P]),
+    "dc_view_score_ld": (c_int, [c_int]),
+    "dc_view_score_workspace": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "dc_view_score": (c_int, [P, c_int, c_int64, c_int, P, P, P, P, c_int64, c_int, c_int, P, c_int, P, c_size_t, P]),
+    "dc_view_weights": (c_int, [P, c_int, P, P, P, P, P, P, P, c_int, c_int64, c_int, c_int, P, P]),
+    "dc_segmented_wmean": (c_int, [P, c_int, c_int, P, P, P, P, P, c_int, c_int, P, P]),
+    "dc_scatter_to_points": (c_int, [P, P, P, P, c_int, c_int64, c_int, c_int, P, P]),
+    "dc_compact_workspace": (c_size_t, [c_int64]),
+    "dc_compact_scan": (c_int, [P, c_int64, P, c_int, P, P, P, c_size_t, P]),
+    "dc_compact_rows": (c_int, [P, c_int64, P, P, c_int64, P, P]),
+    "dc_compact_mask": (c_int, [P, c_int, P, P, P, P, P, P, P, c_int, c_int64, c_int, P, P]),
+    "dc_pixel_fuse": (c_int, [P, P, P, P, P, P, P, P, c_int, P, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int64,
+                              c_int, c_int, c_int, P, P, P]),
+    "dc_pixel_normalize": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, P]),
+    "dc_voxelize_workspace": (c_size_t, [c_int64]),
+    "dc_voxelize": (c_int, [P, P, c_int, c_int64, c_float, P, ctypes.c_int32, P, P, P, P, P, P, c_size_t, P]),
+    "dc_voxel_gather": (c_int, [P, c_int64, P, P, P, c_int, c_int64, P, P]),
+    "dc_row_normalize": (c_int, [P, c_int, c_int64, c_int, c_int, P, P, P]),
+    "dc_ground_init_minmax": (c_int, [P, P]),
+    "dc_ground": (c_int, [P, P, c_int64, P, P, c_int, c_int, c_int, c_float, P, c_int, P, P, P]),
+    "dc_minmax_threshold": (c_int, [P, c_int64, P, c_int, c_float, c_int, P, P]),
+    "dc_backproject": (c_int, [P, c_int, c_int, c_int, P, c_int, c_int, P, P, P]),
+    "dc_points_to_pixels": (c_int, [P, c_int64, P, P, P]),
+    "dc_transform_points": (c_int, [P, c_int64, P, P, P]),
+}
+
+_lib = None
+
+
+class DropClipError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libdropclip error {status}: {message}")
+        self.status = status
+
+
+def load(path: str = LIB_PATH):
+    """Loads the shared library and binds every declared symbol; raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: build it with `python -m dropclip_b200.build` (or __graft_entry__.build()). "
+            "There is no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dc_abi_version() != ABI_VERSION:
+        raise ImportError(f"libdropclip ABI {lib.dc_abi_version()} != expected {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise DropClipError(rc, (load().dc_last_error() or b"").decode())
+
+
+def ptr(t):
+    """Device (or None) pointer of a torch tensor."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def torch_dtype_code(dtype) -> int:
+    import torch
+    return {torch.float16: DC_F16, torch.float32: DC_F32, torch.uint8: DC_U8, torch.int32: DC_I32,
+            torch.int64: DC_I64, torch.float64: DC_F64}[dtype]

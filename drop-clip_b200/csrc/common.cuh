@@ -1,0 +1,72 @@
+// Shared helpers of libdropclip (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dropclip.h"
+
+namespace dc {
+
+// thread-local error message returned by dc_last_error()
+char* error_buffer();
+int fail(int status, const char* fmt, ...);
+
+#define DC_CHECK_ARG(cond, ...)                                         \
+  do {                                                                  \
+    if (!(cond)) return ::dc::fail(DC_ERR_INVALID, __VA_ARGS__);        \
+  } while (0)
+
+#define DC_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return ::dc::fail(DC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                \
+  } while (0)
+
+#define DC_LAUNCH_CHECK() DC_CUDA(cudaGetLastError())
+
+inline cudaStream_t as_stream(dc_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();  // cached per process (device 0 of the current context)
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// torch-style min/max propagate NaN; fminf/fmaxf do not. Used where the reference calls
+// tensor.min()/max().
+__device__ __forceinline__ float nan_min(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b); }
+__device__ __forceinline__ float nan_max(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
+
+// streaming (read-once / write-once) 128-bit accesses that do not pollute L1
+__device__ __forceinline__ int4 ld_stream(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(int4* p, const int4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+}  // namespace dc

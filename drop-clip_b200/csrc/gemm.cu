@@ -1,0 +1,475 @@
+// (3) view scoring and (6) grounding: operand preparation, tcgen05 GEMM launches and epilogues.
+//
+// Reference: utils/feature_fusion.py:311-313 (feat_v_norm @ query.T), models/similarity.py:28-101
+// (vis_feats @ text.T, paired softmax, min-max, threshold), engine/distil.py:244-246.
+#include <mutex>
+
+#include "gemm.cuh"
+
+namespace dc {
+namespace gemm {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+int encode_plane_map(CUtensorMap* out, const void* base, int64_t rows, int k, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(DC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  if (((uintptr_t)base & 15) != 0) return fail(DC_ERR_INVALID, "GEMM operand plane must be 16-byte aligned");
+  if (rows < 1) rows = 1;
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return DC_OK;
+}
+
+}  // namespace gemm
+}  // namespace dc
+
+namespace {
+
+using dc::gemm::Params;
+using dc::gemm::Tile;
+
+// ---------------------------------------------------------------------------- row normalisation
+// One warp per row. torch semantics per dtype:
+//   fp16: norm = fp16(sqrt(sum_fp32 x^2)); y = fp16(float(x) / float(norm))       (rounded twice)
+//   fp32: norm = sqrt(sum_fp32 x^2);       y = x / norm
+// Writes y back in place when `normalize`, and the fp16 operand planes when requested.
+template <typename T, bool kInPlace>
+__global__ void __launch_bounds__(256) row_normalize_kernel(T* __restrict__ x, int64_t n_rows, int dim, int normalize,
+                                                            __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  T* xr = x + row * dim;
+  float inv_scale_num = 1.f;  // divide by this
+  if (normalize) {
+    float ss = 0.f;
+    for (int c = lane; c < dim; c += 32) {
+      const float v = (float)xr[c];
+      ss = fmaf(v, v, ss);
+    }
+    ss = dc::warp_sum(ss);
+    float nrm = sqrtf(ss);
+    if (sizeof(T) == 2) nrm = __half2float(__float2half_rn(nrm));
+    inv_scale_num = nrm;
+  }
+  for (int c = lane; c < dim; c += 32) {
+    float v = (float)xr[c];
+    if (normalize) {
+      v = v / inv_scale_num;  // IEEE division, like torch
+      if (sizeof(T) == 2) v = __half2float(__float2half_rn(v));
+      if (kInPlace) xr[c] = (T)v;
+    }
+    if (hi) {
+      const __half h = __float2half_rn(v);
+      hi[row * dim + c] = h;
+      if (lo) lo[row * dim + c] = __float2half_rn(v - __half2float(h));
+    }
+  }
+}
+
+int launch_row_normalize(void* x, int dtype, int64_t n_rows, int dim, int normalize, bool in_place, void* hi, void* lo,
+                         cudaStream_t st) {
+  if (n_rows <= 0) return DC_OK;
+  const unsigned grid = (unsigned)dc::ceil_div<int64_t>(n_rows, 8);
+  if (dtype == DC_F16) {
+    if (in_place) row_normalize_kernel<__half, true><<<grid, 256, 0, st>>>((__half*)x, n_rows, dim, normalize, (__half*)hi, nullptr);
+    else row_normalize_kernel<__half, false><<<grid, 256, 0, st>>>((__half*)x, n_rows, dim, normalize, (__half*)hi, nullptr);
+  } else {
+    if (in_place) row_normalize_kernel<float, true><<<grid, 256, 0, st>>>((float*)x, n_rows, dim, normalize, (__half*)hi, (__half*)lo);
+    else row_normalize_kernel<float, false><<<grid, 256, 0, st>>>((float*)x, n_rows, dim, normalize, (__half*)hi, (__half*)lo);
+  }
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+// ---------------------------------------------------------------------------- epilogues
+// raw store: out[row, col] for valid rows/cols
+struct EpiStore {
+  float* out;
+  int ld;
+  __device__ __forceinline__ void row(const Tile& t, int r, int c0, const float (&v)[32]) {
+    if (r >= t.rows) return;
+    float* dst = out + (int64_t)(t.a_row + r) * ld + c0;
+    const int n = min(32, min(t.cols, ld) - c0);
+    if (n == 32 && (ld & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < n) dst[i] = v[i];
+    }
+  }
+  __device__ __forceinline__ void finish_row(const Tile&, int) {}
+  __device__ __forceinline__ void finish_warp() {}
+};
+
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+  v += 0.0f;
+  if (v >= 0) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+  v += 0.0f;
+  if (v >= 0) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+
+// Grounding epilogue. Every thread owns one point (row); the prompt axis is walked in 32-column
+// chunks, so the N x P similarity matrix never leaves the SM unless mode == RAW.
+struct EpiGround {
+  int mode;
+  int n_prompts;
+  float inv_temp;
+  float* out;
+  int out_ld;
+  uint8_t* pred;
+  float* minmax;  // [0] min(out) [1] max(out) [2] min(raw) [3] max(raw)
+  // per-thread running state
+  float pos, acc, neg_max, raw_min, raw_max;
+  float out_min, out_max;
+  bool have;
+
+  __device__ __forceinline__ void row(const Tile& t, int r, int c0, const float (&v)[32]) {
+    if (c0 == 0) {
+      pos = v[0];
+      acc = 0.f;
+      neg_max = -INFINITY;
+      raw_min = INFINITY;
+      raw_max = -INFINITY;
+    }
+    if (r >= t.rows) return;
+    const int n = min(32, n_prompts - c0);
+    if (mode == DC_GROUND_RAW) {
+      float* dst = out + (int64_t)(t.a_row + r) * out_ld + c0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < n) {
+          dst[i] = v[i];
+          raw_min = fminf(raw_min, v[i]);
+          raw_max = fmaxf(raw_max, v[i]);
+        }
+      return;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i < n) {
+        raw_min = fminf(raw_min, v[i]);
+        raw_max = fmaxf(raw_max, v[i]);
+        if (c0 + i > 0) {
+          if (mode == DC_GROUND_PAIRED) acc += __expf((v[i] - pos) * inv_temp);
+          else { acc += v[i]; neg_max = fmaxf(neg_max, v[i]); }
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void finish_row(const Tile& t, int r) {
+    have = r < t.rows;
+    if (!have) return;
+    const int64_t gr = (int64_t)t.a_row + r;
+    float o;
+    if (mode == DC_GROUND_RAW) {
+      out_min = raw_min;
+      out_max = raw_max;
+      return;
+    }
+    const float n_neg = (float)(n_prompts - 1);
+    if (mode == DC_GROUND_PAIRED) {
+      o = 1.f / (n_neg + acc);
+      if (o != o) o = 0.f;  // nan_to_num
+    } else {
+      o = pos - acc / n_neg;
+      pred[gr] = (pos >= neg_max) ? 1 : 0;  // argmax == 0 (first index wins ties)
+    }
+    out[gr] = o;
+    out_min = o;
+    out_max = o;
+  }
+  __device__ __forceinline__ void finish_warp() {
+    float a = have ? out_min : INFINITY, b = have ? out_max : -INFINITY;
+    float c = have ? raw_min : INFINITY, d = have ? raw_max : -INFINITY;
+    a = dc::warp_min(a); b = dc::warp_max(b); c = dc::warp_min(c); d = dc::warp_max(d);
+    if ((threadIdx.x & 31) == 0) {
+      if (a != INFINITY) atomic_min_f(minmax + 0, a);
+      if (b != -INFINITY) atomic_max_f(minmax + 1, b);
+      if (c != INFINITY) atomic_min_f(minmax + 2, c);
+      if (d != -INFINITY) atomic_max_f(minmax + 3, d);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------- view-score helpers
+// Tile list: every scene's feature rows cut into 128-row tiles, B tile = that scene's queries.
+__global__ void build_score_tiles_kernel(const int64_t* __restrict__ feat_off, const int64_t* __restrict__ view_off,
+                                         const int64_t* __restrict__ query_off, int n_scenes, int4* __restrict__ tiles,
+                                         int* __restrict__ tile_count, int max_tiles) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int n = 0;
+  for (int s = 0; s < n_scenes; ++s) {
+    const int64_t r0 = feat_off[view_off[s]], r1 = feat_off[view_off[s + 1]];
+    const int q = (int)(query_off[s + 1] - query_off[s]);
+    for (int64_t r = r0; r < r1; r += dc::gemm::kBlockM) {
+      if (n < max_tiles) tiles[n] = make_int4((int)r, (int)query_off[s], (int)min((int64_t)dc::gemm::kBlockM, r1 - r), q);
+      ++n;
+    }
+  }
+  *tile_count = n < max_tiles ? n : max_tiles;
+}
+
+// One warp per view: global min/max of the view's (rows x Q) block, then the weight of each bound row.
+__global__ void __launch_bounds__(128) view_weights_kernel(
+    const float* __restrict__ sims, int sims_ld, const int64_t* __restrict__ feat_off, const int32_t* __restrict__ view_scene,
+    const int64_t* __restrict__ view_off, const int64_t* __restrict__ query_off, const int64_t* __restrict__ wobj_off,
+    const int32_t* __restrict__ row_object, const uint32_t* __restrict__ counts, int nbins, int64_t total_views,
+    int sim_kernel, int use_visibility, float* __restrict__ weight_obj) {
+  const int64_t g = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (g >= total_views) return;
+  const int lane = threadIdx.x & 31;
+  const int s = view_scene[g];
+  const int n_q = (int)(query_off[s + 1] - query_off[s]);
+  const int n_v = (int)(view_off[s + 1] - view_off[s]);
+  const int v_local = (int)(g - view_off[s]);
+  const int64_t r0 = feat_off[g], r1 = feat_off[g + 1];
+  float* w_scene = weight_obj + wobj_off[s];
+  float mn = INFINITY, mx = -INFINITY;
+  bool any_nan = false;
+  if (sim_kernel != DC_SIM_NONE) {
+    const int64_t cells = (r1 - r0) * n_q;
+    for (int64_t i = lane; i < cells; i += 32) {
+      const float v = sims[(r0 + i / n_q) * sims_ld + (i % n_q)];
+      any_nan |= (v != v);
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+    }
+    mn = dc::warp_min(mn);
+    mx = dc::warp_max(mx);
+    any_nan = __any_sync(0xffffffffu, any_nan);
+    if (any_nan) mn = mx = __int_as_float(0x7fc00000);  // torch min()/max() propagate NaN
+  }
+  const float range = mx - mn;
+  for (int64_t r = r0 + lane; r < r1; r += 32) {
+    const int obj = row_object[r];
+    if (obj < 0) continue;
+    float w = 1.0f;
+    if (use_visibility) w = (float)counts[g * nbins + obj];
+    if (sim_kernel != DC_SIM_NONE) {
+      const float* srow = sims + r * sims_ld;
+      const float pos = (srow[obj] - mn) / range;
+      float red = (sim_kernel == DC_SIM_MAX) ? -INFINITY : 0.f;
+      bool nan_seen = false;
+      for (int o = 0; o < n_q; ++o) {
+        if (o == obj) continue;
+        const float v = (srow[o] - mn) / range;
+        nan_seen |= (v != v);
+        if (sim_kernel == DC_SIM_MAX) red = fmaxf(red, v);
+        else red += v;
+      }
+      if (sim_kernel == DC_SIM_MEAN) red = red / (float)(n_q - 1);
+      if (nan_seen) red = __int_as_float(0x7fc00000);
+      w = pos - red;
+      // torch.clip(x, min=eps): NaN stays NaN
+      if (w == w) w = fmaxf(w, 1e-6f);
+    }
+    w_scene[(int64_t)obj * n_v + v_local] = w;
+  }
+}
+
+__global__ void init_minmax_kernel(float* m) {
+  if (threadIdx.x == 0) { m[0] = INFINITY; m[1] = -INFINITY; m[2] = INFINITY; m[3] = -INFINITY; }
+}
+
+__global__ void __launch_bounds__(256) minmax_threshold_kernel(float* __restrict__ v, int64_t n, const float* __restrict__ mm,
+                                                               int use_raw, float thr, int pred_from_thr,
+                                                               uint8_t* __restrict__ pred) {
+  const float mn = mm[0], mx = mm[1];
+  const bool differ = use_raw ? (mm[3] != mm[2]) : (mx != mn);
+  const float range = mx - mn;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float x = v[i];
+    x = differ ? (x - mn) / range : x / mx;
+    v[i] = x;
+    if (pred_from_thr) pred[i] = x > thr ? 1 : 0;
+  }
+}
+
+template <class Epi>
+int launch_bn(int bn, const void* a_hi, const void* a_lo, int64_t a_rows, const void* b_hi, const void* b_lo, int64_t b_rows,
+              const Params& p, const Epi& epi, int max_tiles, cudaStream_t st) {
+  switch (bn) {
+    case 32: return dc::gemm::launch<32>(a_hi, a_lo, a_rows, b_hi, b_lo, b_rows, p, epi, max_tiles, st);
+    case 64: return dc::gemm::launch<64>(a_hi, a_lo, a_rows, b_hi, b_lo, b_rows, p, epi, max_tiles, st);
+    case 128: return dc::gemm::launch<128>(a_hi, a_lo, a_rows, b_hi, b_lo, b_rows, p, epi, max_tiles, st);
+    case 256: return dc::gemm::launch<256>(a_hi, a_lo, a_rows, b_hi, b_lo, b_rows, p, epi, max_tiles, st);
+  }
+  return dc::fail(DC_ERR_UNSUPPORTED, "unsupported GEMM N tile %d", bn);
+}
+
+int pick_bn(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct ScoreWorkspace {
+  size_t a_hi, a_lo, q_hi, q_lo, tiles, tile_count, total;
+  int max_tiles;
+};
+
+ScoreWorkspace score_layout(int64_t total_rows, int64_t total_queries, int dim, int feat_dtype, int n_scenes_bound) {
+  ScoreWorkspace w{};
+  size_t off = 0;
+  const size_t a_bytes = align_up((size_t)(total_rows > 0 ? total_rows : 1) * dim * 2, 1024);
+  const size_t q_bytes = align_up((size_t)(total_queries > 0 ? total_queries : 1) * dim * 2, 1024);
+  w.a_hi = off; off += a_bytes;
+  w.a_lo = off; off += (feat_dtype == DC_F32) ? a_bytes : 0;
+  w.q_hi = off; off += q_bytes;
+  w.q_lo = off; off += q_bytes;
+  w.max_tiles = (int)(total_rows / dc::gemm::kBlockM + n_scenes_bound + 1);
+  w.tiles = off; off += align_up(sizeof(int4) * (size_t)w.max_tiles, 1024);
+  w.tile_count = off; off += 1024;
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dc_view_score_ld(int max_queries_per_scene) { return pick_bn(max_queries_per_scene); }
+
+size_t dc_view_score_workspace(int64_t total_rows, int64_t total_queries, int dim, int feat_dtype) {
+  // the tile list is bounded with total_queries >= n_scenes
+  return score_layout(total_rows, total_queries, dim, feat_dtype, (int)total_queries).total;
+}
+
+int dc_view_score(const void* feats, int feat_dtype, int64_t total_rows, int dim, const int64_t* feat_off,
+                  const int64_t* view_off, const float* queries, const int64_t* query_off, int64_t total_queries,
+                  int n_scenes, int max_queries_per_scene, float* sims, int sims_ld, void* workspace,
+                  size_t workspace_bytes, dc_stream_t stream) {
+  DC_CHECK_ARG(feats && feat_off && view_off && queries && query_off && sims && workspace,
+               "dc_view_score: null pointer argument");
+  DC_CHECK_ARG(feat_dtype == DC_F16 || feat_dtype == DC_F32, "dc_view_score: features must be fp16 or fp32");
+  DC_CHECK_ARG(dim > 0 && dim % 64 == 0, "dc_view_score: feature dim must be a multiple of 64 (got %d)", dim);
+  DC_CHECK_ARG(max_queries_per_scene >= 1 && max_queries_per_scene <= 256, "dc_view_score: 1..256 queries per scene");
+  const int bn = pick_bn(max_queries_per_scene);
+  DC_CHECK_ARG(sims_ld >= bn, "dc_view_score: sims_ld must be >= %d", bn);
+  DC_CHECK_ARG(((uintptr_t)workspace & 1023) == 0, "dc_view_score: workspace must be 1024-byte aligned");
+  DC_CHECK_ARG(total_rows < (1ll << 31) && total_queries < (1ll << 31), "dc_view_score: too many rows");
+  if (total_rows <= 0 || n_scenes <= 0) return DC_OK;
+  const ScoreWorkspace w = score_layout(total_rows, total_queries, dim, feat_dtype, (int)total_queries);
+  if (workspace_bytes < w.total)
+    return dc::fail(DC_ERR_WORKSPACE, "dc_view_score: workspace %zu < %zu", workspace_bytes, w.total);
+  cudaStream_t st = dc::as_stream(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  void* a_hi = ws + w.a_hi;
+  void* a_lo = feat_dtype == DC_F32 ? ws + w.a_lo : nullptr;
+  void* q_hi = ws + w.q_hi;
+  void* q_lo = ws + w.q_lo;
+  int rc;
+  // normalised copies of the feature rows (the reference keeps feat_v itself un-normalised, :311,333)
+  if ((rc = launch_row_normalize(const_cast<void*>(feats), feat_dtype, total_rows, dim, 1, false, a_hi, a_lo, st))) return rc;
+  if ((rc = launch_row_normalize(const_cast<float*>(queries), DC_F32, total_queries, dim, 0, false, q_hi, q_lo, st))) return rc;
+  int4* tiles = reinterpret_cast<int4*>(ws + w.tiles);
+  int* tile_count = reinterpret_cast<int*>(ws + w.tile_count);
+  build_score_tiles_kernel<<<1, 32, 0, st>>>(feat_off, view_off, query_off, n_scenes, tiles, tile_count, w.max_tiles);
+  DC_LAUNCH_CHECK();
+  Params p{tiles, tile_count, total_rows, bn, dim, feat_dtype == DC_F32 ? 3 : 2};
+  EpiStore epi{sims, sims_ld};
+  return launch_bn(bn, a_hi, a_lo, total_rows, q_hi, q_lo, total_queries, p, epi, w.max_tiles, st);
+}
+
+int dc_view_weights(const float* sims, int sims_ld, const int64_t* feat_off, const int32_t* view_scene,
+                    const int64_t* view_off, const int64_t* query_off, const int64_t* wobj_off,
+                    const int32_t* row_object, const uint32_t* counts, int nbins, int64_t total_views,
+                    int sim_kernel, int use_visibility, float* weight_obj, dc_stream_t stream) {
+  DC_CHECK_ARG(feat_off && view_scene && view_off && query_off && wobj_off && row_object && weight_obj,
+               "dc_view_weights: null pointer argument");
+  DC_CHECK_ARG(sim_kernel == DC_SIM_NONE || sims, "dc_view_weights: sims required for a similarity kernel");
+  DC_CHECK_ARG(!use_visibility || counts, "dc_view_weights: counts required for use_visibility");
+  DC_CHECK_ARG(sim_kernel >= DC_SIM_NONE && sim_kernel <= DC_SIM_MEAN, "dc_view_weights: Please set method in [mean, max]");
+  if (total_views <= 0) return DC_OK;
+  view_weights_kernel<<<(unsigned)dc::ceil_div<int64_t>(total_views, 4), 128, 0, dc::as_stream(stream)>>>(
+      sims, sims_ld, feat_off, view_scene, view_off, query_off, wobj_off, row_object, counts, nbins, total_views,
+      sim_kernel, use_visibility, weight_obj);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+int dc_row_normalize(void* x, int dtype, int64_t n_rows, int dim, int normalize, void* plane_hi, void* plane_lo,
+                     dc_stream_t stream) {
+  DC_CHECK_ARG(x, "dc_row_normalize: null pointer argument");
+  DC_CHECK_ARG(dtype == DC_F16 || dtype == DC_F32, "dc_row_normalize: dtype must be fp16 or fp32");
+  DC_CHECK_ARG(dim > 0, "dc_row_normalize: bad dim");
+  DC_CHECK_ARG(!plane_lo || plane_hi, "dc_row_normalize: plane_lo needs plane_hi");
+  return launch_row_normalize(x, dtype, n_rows, dim, normalize, true, plane_hi, dtype == DC_F32 ? plane_lo : nullptr,
+                              dc::as_stream(stream));
+}
+
+int dc_ground_init_minmax(float* minmax, dc_stream_t stream) {
+  DC_CHECK_ARG(minmax, "dc_ground_init_minmax: null pointer argument");
+  init_minmax_kernel<<<1, 32, 0, dc::as_stream(stream)>>>(minmax);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+int dc_ground(const void* x_hi, const void* x_lo, int64_t n_points, const void* t_hi, const void* t_lo, int n_prompts,
+              int dim, int mode, float softmax_temp, float* out, int out_ld, uint8_t* pred, float* minmax,
+              dc_stream_t stream) {
+  DC_CHECK_ARG(x_hi && t_hi && out && minmax, "dc_ground: null pointer argument");
+  DC_CHECK_ARG(n_prompts >= 1 && n_prompts <= 256, "dc_ground: 1..256 prompts per call (got %d)", n_prompts);
+  DC_CHECK_ARG(dim > 0 && dim % 64 == 0, "dc_ground: feature dim must be a multiple of 64 (got %d)", dim);
+  DC_CHECK_ARG(mode >= DC_GROUND_RAW && mode <= DC_GROUND_ARGMAX, "dc_ground: bad mode");
+  DC_CHECK_ARG(mode != DC_GROUND_ARGMAX || pred, "dc_ground: argmax mode needs pred");
+  DC_CHECK_ARG(mode == DC_GROUND_RAW || n_prompts >= 2, "dc_ground: paired/argmax need at least one negative prompt");
+  DC_CHECK_ARG(mode != DC_GROUND_RAW || out_ld >= n_prompts, "dc_ground: out_ld < n_prompts");
+  DC_CHECK_ARG(n_points < (1ll << 31), "dc_ground: too many points for one call");
+  if (n_points <= 0) return DC_OK;
+  const int bn = pick_bn(n_prompts);
+  const int n_terms = x_lo ? 3 : (t_lo ? 2 : 1);
+  Params p{nullptr, nullptr, n_points, n_prompts, dim, n_terms};
+  EpiGround epi{};
+  epi.mode = mode;
+  epi.n_prompts = n_prompts;
+  epi.inv_temp = 1.0f / softmax_temp;
+  epi.out = out;
+  epi.out_ld = out_ld;
+  epi.pred = pred;
+  epi.minmax = minmax;
+  const int max_tiles = (int)dc::ceil_div<int64_t>(n_points, dc::gemm::kBlockM);
+  return launch_bn(bn, x_hi, x_lo, n_points, t_hi, t_lo ? t_lo : t_hi, n_prompts, p, epi, max_tiles, dc::as_stream(stream));
+}
+
+int dc_minmax_threshold(float* values, int64_t n, const float* minmax, int use_raw_extrema_for_test, float threshold,
+                        int pred_from_threshold, uint8_t* pred, dc_stream_t stream) {
+  DC_CHECK_ARG(values && minmax, "dc_minmax_threshold: null pointer argument");
+  DC_CHECK_ARG(!pred_from_threshold || pred, "dc_minmax_threshold: pred required");
+  if (n <= 0) return DC_OK;
+  const int64_t blocks = dc::ceil_div<int64_t>(n, 256);
+  const unsigned grid = (unsigned)(blocks < (int64_t)dc::sm_count() * 8 ? blocks : (int64_t)dc::sm_count() * 8);
+  minmax_threshold_kernel<<<grid, 256, 0, dc::as_stream(stream)>>>(values, n, minmax, use_raw_extrema_for_test, threshold,
+                                                                  pred_from_threshold, pred);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,521 @@
+"""Scene-batched device engine under the reference-shaped classes.
+
+A `SceneBatch` holds a ragged batch of scenes in HBM in the layout the C ABI takes
+(concatenated arrays + int64 prefix offsets); `FusionEngine` strings the CUDA
+kernels together on the current stream. The reference processes one scene per call and one
+view per Python iteration (utils/feature_fusion.py:88,303); one scene is only ~10^2 MB of
+traffic, so batching scenes is what lets the kernels run at HBM speed instead of launch speed.
+torch is used for allocation, streams and copies only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, current_stream, ptr
+
+SIM_KERNELS = {None: _lib.DC_SIM_NONE, "max": _lib.DC_SIM_MAX, "mean": _lib.DC_SIM_MEAN}
+MAX_BINS = 256  # instance ids are stored as uint8 labels downstream (tools/preprocess_data.py:294)
+
+
+def _prefix(counts: Sequence[int]) -> np.ndarray:
+    out = np.zeros(len(counts) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(counts, dtype=np.int64), out=out[1:])
+    return out
+
+
+def intrinsic_matrix(intr: Dict[str, float]) -> np.ndarray:
+    """utils/feature_fusion.py:35-40, always promoted to fp64 (K @ fp64 points is fp64 anyway)."""
+    return np.asarray([[intr["fx"], 0, intr["cx"]], [0, intr["fy"], intr["cy"]], [0, 0, 1]], dtype=np.float64)
+
+
+@dataclass
+class SceneBatch:
+    """Ragged scene batch resident on one GPU."""
+
+    device: torch.device
+    height: int
+    width: int
+    n_scenes: int
+    # host-side extents
+    n_points: List[int]
+    n_views: List[int]
+    n_queries: List[int]
+    feat_rows: List[int]  # per view (stacked over scenes)
+    # device arrays
+    points: torch.Tensor  # (sum N, 3) f64
+    depths: torch.Tensor  # (TV, H, W) f32
+    inv_poses: torch.Tensor  # (TV, 16) f32
+    intrinsics: torch.Tensor  # (S, 9) f64
+    segs: Optional[torch.Tensor] = None  # (TV, H, W) u8 / i32 / i64
+    labels: Optional[torch.Tensor] = None  # (sum N,) i64
+    feats: Optional[torch.Tensor] = None  # (TR, C) f16 / f32  or (TV, ph, pw, C) f32 for the pixel path
+    queries: Optional[torch.Tensor] = None  # (sum Q, C) f32
+    # offsets (device int64) + host mirrors
+    off: Dict[str, torch.Tensor] = field(default_factory=dict)
+    off_host: Dict[str, np.ndarray] = field(default_factory=dict)
+
+    @property
+    def total_points(self) -> int:
+        return int(self.off_host["point"][-1])
+
+    @property
+    def total_views(self) -> int:
+        return int(self.off_host["view"][-1])
+
+    @property
+    def total_queries(self) -> int:
+        return int(self.off_host["query"][-1])
+
+    @property
+    def total_rows(self) -> int:
+        return int(self.off_host["feat"][-1])
+
+    def h2d_bytes(self) -> int:
+        n = 0
+        for t in (self.points, self.depths, self.inv_poses, self.intrinsics, self.segs, self.labels, self.feats,
+                  self.queries):
+            if t is not None:
+                n += t.numel() * t.element_size()
+        for t in self.off.values():
+            n += t.numel() * t.element_size()
+        return n
+
+    @staticmethod
+    def offsets_for(n_points, n_views, n_queries, feat_rows):
+        host = {
+            "point": _prefix(n_points),
+            "view": _prefix(n_views),
+            "query": _prefix(n_queries),
+            "mask": _prefix([v * n for v, n in zip(n_views, n_points)]),
+            "wobj": _prefix([q * v for q, v in zip(n_queries, n_views)]),
+            "feat": _prefix(feat_rows),
+        }
+        host["view_scene"] = np.repeat(np.arange(len(n_views), dtype=np.int32), np.asarray(n_views, dtype=np.int64))
+        return host
+
+    @classmethod
+    def from_host(cls, scenes: Sequence, device="cuda", pixel_features: bool = False,
+                  inv_poses: Optional[Sequence] = None, staging: Optional["PinnedStaging"] = None) -> "SceneBatch":
+        """Uploads scenes given in the reference's own containers (numpy arrays and lists, torch
+        feature tensors). `scenes[i]` needs attributes/keys points, depths, camera_poses, intrinsic
+        and optionally labels, seg_masks, mv_features, query_embeddings.
+
+        The camera->world poses are inverted here with np.linalg.inv in their own dtype, exactly
+        like utils/transforms.py:54 does on the host (a 4x4 per view)."""
+        dev = torch.device(device)
+        get = (lambda s, k: s.get(k)) if isinstance(scenes[0], dict) else (lambda s, k: getattr(s, k, None))
+        intr0 = get(scenes[0], "intrinsic")
+        H, W = int(intr0["height"]), int(intr0["width"])
+        n_points = [int(np.asarray(get(s, "points")).shape[0]) for s in scenes]
+        n_views = [len(get(s, "depths")) for s in scenes]
+        has_q = get(scenes[0], "query_embeddings") is not None
+        has_f = get(scenes[0], "mv_features") is not None
+        n_queries = [int(get(s, "query_embeddings").shape[0]) if has_q else 0 for s in scenes]
+        feat_rows: List[int] = []
+        if has_f and not pixel_features:
+            for s in scenes:
+                feat_rows += [int(f.shape[0]) for f in get(s, "mv_features")]
+        else:
+            feat_rows = [0] * sum(n_views)
+        host = cls.offsets_for(n_points, n_views, n_queries, feat_rows)
+        if staging is not None:
+            staging.begin()
+        up = staging.upload if staging is not None else (lambda a: torch.as_tensor(a).to(dev, non_blocking=False))
+
+        pts = np.concatenate([np.ascontiguousarray(get(s, "points"), dtype=np.float64).reshape(-1, 3) for s in scenes])
+        dlist = [d for s in scenes for d in get(s, "depths")]
+        if staging is not None and dlist:
+            depths_dev = staging.upload_list(dlist, torch.float32, (H, W))
+        else:
+            depths = np.stack([np.asarray(d, dtype=np.float32) for d in dlist]) if dlist else np.zeros((0, H, W), np.float32)
+            depths_dev = None
+        if inv_poses is None:
+            inv = [np.linalg.inv(np.asarray(p)) for s in scenes for p in get(s, "camera_poses")]
+        else:
+            inv = [np.asarray(p) for ps in inv_poses for p in ps]
+        inv = np.stack(inv).astype(np.float32).reshape(-1, 16) if inv else np.zeros((0, 16), np.float32)
+        K = np.stack([intrinsic_matrix(get(s, "intrinsic")).reshape(9) for s in scenes])
+        b = cls(device=dev, height=H, width=W, n_scenes=len(scenes), n_points=n_points, n_views=n_views,
+                n_queries=n_queries, feat_rows=feat_rows, points=up(pts),
+                depths=depths_dev if depths_dev is not None else up(depths), inv_poses=up(inv), intrinsics=up(K))
+        if get(scenes[0], "seg_masks") is not None:
+            segs = [np.asarray(m) for s in scenes for m in get(s, "seg_masks")]
+            if segs:
+                dt = segs[0].dtype
+                if dt not in (np.uint8, np.int32, np.int64):
+                    dt = np.int64
+                if staging is not None:
+                    tdt = {np.dtype(np.uint8): torch.uint8, np.dtype(np.int32): torch.int32,
+                           np.dtype(np.int64): torch.int64}[np.dtype(dt)]
+                    b.segs = staging.upload_list(segs, tdt, (H, W))
+                else:
+                    b.segs = up(np.stack([m.astype(dt, copy=False) for m in segs]))
+        if get(scenes[0], "labels") is not None:
+            b.labels = up(np.concatenate([np.asarray(get(s, "labels")).astype(np.int64).reshape(-1) for s in scenes]))
+        if has_f:
+            fl = [f for s in scenes for f in get(s, "mv_features")]
+            if pixel_features:
+                b.feats = torch.stack([f.to(dev, torch.float32) for f in fl]).contiguous()
+            else:
+                dt = torch.float16 if fl[0].dtype == torch.float16 else torch.float32
+                if fl and fl[0].is_cuda:
+                    b.feats = torch.cat([f.to(dt) for f in fl]).to(dev).contiguous()
+                elif fl:
+                    b.feats = up(torch.cat([f.to(dt) for f in fl]))
+        if has_q:
+            ql = [get(s, "query_embeddings").to(torch.float32) for s in scenes]
+            b.queries = torch.cat(ql).to(dev).contiguous() if ql[0].is_cuda else up(torch.cat(ql))
+        b.off_host = host
+        b.off = {k: up(v) for k, v in host.items()}
+        if staging is not None:
+            staging.end()
+        return b
+
+
+def batch_from_device(scenes: Sequence[dict], device="cuda", seg_dtype=torch.int64) -> SceneBatch:
+    """Builds a SceneBatch from scenes that already live on the GPU (`scenes.make_scene(...,
+    as_torch=True)`): used by the benchmark so that synthetic data never crosses PCIe. The
+    inverse poses are still taken on the host with np.linalg.inv (4x4 per view), as in
+    utils/transforms.py:54."""
+    dev = torch.device(device)
+    intr0 = scenes[0]["intrinsic"]
+    H, W = int(intr0["height"]), int(intr0["width"])
+    n_points = [int(s["points"].shape[0]) for s in scenes]
+    n_views = [int(s["depths"].shape[0]) for s in scenes]
+    n_queries = [int(s["query_embeddings"].shape[0]) for s in scenes]
+    feat_rows = [int(f.shape[0]) for s in scenes for f in s["mv_features"]]
+    host = SceneBatch.offsets_for(n_points, n_views, n_queries, feat_rows)
+    inv = np.stack([np.linalg.inv(p) for s in scenes for p in s["camera_poses"].cpu().numpy()]).astype(np.float32)
+    K = np.stack([intrinsic_matrix(s["intrinsic"]).reshape(9) for s in scenes])
+    fdt = scenes[0]["mv_features"][0].dtype
+    b = SceneBatch(
+        device=dev, height=H, width=W, n_scenes=len(scenes), n_points=n_points, n_views=n_views, n_queries=n_queries,
+        feat_rows=feat_rows,
+        points=torch.cat([s["points"] for s in scenes]).to(dev, torch.float64).contiguous(),
+        depths=torch.cat([s["depths"] for s in scenes]).to(dev, torch.float32).contiguous(),
+        inv_poses=torch.from_numpy(inv.reshape(-1, 16)).to(dev), intrinsics=torch.from_numpy(K).to(dev),
+        segs=torch.cat([s["seg_masks"].to(seg_dtype) for s in scenes]).to(dev).contiguous(),
+        labels=torch.cat([s["labels"] for s in scenes]).to(dev, torch.int64).contiguous(),
+        feats=torch.cat([f.to(fdt) for s in scenes for f in s["mv_features"]]).to(dev).contiguous(),
+        queries=torch.cat([s["query_embeddings"] for s in scenes]).to(dev, torch.float32).contiguous())
+    b.off_host = host
+    b.off = {k: torch.from_numpy(v).to(dev) for k, v in host.items()}
+    return b
+
+
+class PinnedStaging:
+    """Reusable pinned host buffers so that host->device copies of numpy inputs run at PCIe speed
+    and asynchronously on the current stream. Slots are handed out in call order between
+    begin() and end(); begin() waits until the copies of the previous round have drained before
+    the buffers are overwritten."""
+
+    def __init__(self, device="cuda"):
+        self.device = torch.device(device)
+        self._bufs: List[torch.Tensor] = []
+        self._slot = 0
+        self._event: Optional[torch.cuda.Event] = None
+        self.bytes_uploaded = 0
+
+    def begin(self):
+        if self._event is not None:
+            self._event.synchronize()
+        self._slot = 0
+
+    def end(self):
+        self._event = torch.cuda.Event()
+        self._event.record()
+
+    def upload_list(self, arrays, dtype: torch.dtype, item_shape) -> torch.Tensor:
+        """Stacks a list of equally-shaped host arrays straight into one pinned buffer (one host
+        copy per array instead of np.stack + a second copy) and uploads it."""
+        n = len(arrays)
+        numel = int(np.prod(item_shape)) if len(item_shape) else 1
+        if self._slot == len(self._bufs):
+            self._bufs.append(torch.empty(max(n * numel, 1), dtype=dtype, pin_memory=True))
+        buf = self._bufs[self._slot]
+        if buf.dtype != dtype or buf.numel() < n * numel:
+            buf = torch.empty(max(n * numel, 1), dtype=dtype, pin_memory=True)
+            self._bufs[self._slot] = buf
+        self._slot += 1
+        view = buf[: n * numel].view((n,) + tuple(item_shape))
+        for i, a in enumerate(arrays):
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a))
+            view[i].copy_(t.reshape(item_shape))  # converts dtype if needed
+        self.bytes_uploaded += n * numel * buf.element_size()
+        return view.to(self.device, non_blocking=True)
+
+    def upload(self, arr) -> torch.Tensor:
+        t = arr if isinstance(arr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(arr))
+        t = t.contiguous()
+        if self._slot == len(self._bufs):
+            self._bufs.append(torch.empty(max(t.numel(), 1), dtype=t.dtype, pin_memory=True))
+        buf = self._bufs[self._slot]
+        if buf.dtype != t.dtype or buf.numel() < t.numel():
+            buf = torch.empty(max(t.numel(), 1), dtype=t.dtype, pin_memory=True)
+            self._bufs[self._slot] = buf
+        self._slot += 1
+        view = buf[:t.numel()].view(t.shape)
+        view.copy_(t)
+        self.bytes_uploaded += t.numel() * t.element_size()
+        return view.to(self.device, non_blocking=True)
+
+
+class FusionEngine:
+    """Launch sequences over a SceneBatch. Every method only enqueues work on the current stream."""
+
+    def __init__(self, device="cuda"):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("dropclip_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device(device)
+        self.launches = 0  # kernels launched by this engine (bench.py's gpu_launches)
+        self.profile: Optional[Dict[str, list]] = None  # name -> [(start_event, end_event)] when enabled
+
+    def _tick(self, name: str):
+        """Context manager recording CUDA events around a launch group on the current stream."""
+        eng = self
+
+        class _T:
+            def __enter__(self_inner):
+                if eng.profile is not None:
+                    self_inner.a = torch.cuda.Event(enable_timing=True)
+                    self_inner.b = torch.cuda.Event(enable_timing=True)
+                    self_inner.a.record()
+                return self_inner
+
+            def __exit__(self_inner, *exc):
+                if eng.profile is not None:
+                    self_inner.b.record()
+                    eng.profile.setdefault(name, []).append((self_inner.a, self_inner.b))
+                return False
+
+        return _T()
+
+    def profile_ms(self) -> Dict[str, float]:
+        """Mean duration per recorded launch group (call after a synchronize)."""
+        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in (self.profile or {}).items()}
+
+    # ------------------------------------------------------------------ (1)+(2)
+    def visibility(self, b: SceneBatch, threshold: float = 0.05, mask_dtype=torch.uint8, point_object: bool = False):
+        """Returns (mask [flat, mask layout], any_visible [sum N] u8, point_object | None)."""
+        total_mask = int(b.off_host["mask"][-1])
+        mask = torch.empty(total_mask, dtype=mask_dtype, device=b.device)
+        any_vis = torch.empty(b.total_points, dtype=torch.uint8, device=b.device)
+        pobj = torch.empty(total_mask, dtype=torch.int32, device=b.device) if point_object else None
+        segs = b.segs if point_object else None
+        with self._tick("project_visibility"):
+            check(self.lib.dc_project_visibility(
+                ptr(b.points), ptr(b.off["point"]), ptr(b.off["view"]), ptr(b.depths), ptr(b.inv_poses), ptr(b.intrinsics),
+                ptr(b.off["mask"]), b.n_scenes, max(b.n_points, default=0), max(b.n_views, default=0), b.height, b.width,
+                float(threshold), ptr(mask), mask.element_size(), ptr(any_vis), ptr(segs),
+                _lib.torch_dtype_code(segs.dtype) if segs is not None else _lib.DC_I64, ptr(pobj), current_stream()))
+        self.launches += 1
+        return mask, any_vis, pobj
+
+    def seg_tables(self, b: SceneBatch):
+        """Instance histograms and the feature-row <-> object binding of every view."""
+        tv = b.total_views
+        counts = torch.empty((tv, MAX_BINS), dtype=torch.int32, device=b.device)
+        outside = torch.empty(tv, dtype=torch.int32, device=b.device)
+        with self._tick("seg_histogram"):
+            check(self.lib.dc_seg_histogram(ptr(b.segs), _lib.torch_dtype_code(b.segs.dtype), tv, b.height * b.width,
+                                            MAX_BINS, ptr(counts), ptr(outside), current_stream()))
+        row_object = torch.empty(max(b.total_rows, 1), dtype=torch.int32, device=b.device)
+        total_wobj = int(b.off_host["wobj"][-1])
+        object_row = torch.empty(max(total_wobj, 1), dtype=torch.int32, device=b.device)
+        status = torch.empty(max(tv, 1), dtype=torch.int32, device=b.device)
+        check(self.lib.dc_view_table(ptr(counts), ptr(outside), ptr(b.off["feat"]), ptr(b.off["view_scene"]),
+                                     ptr(b.off["view"]), ptr(b.off["query"]), ptr(b.off["wobj"]), tv, b.total_rows,
+                                     total_wobj, MAX_BINS, ptr(row_object), ptr(object_row), ptr(status),
+                                     current_stream()))
+        self.launches += 2
+        return counts, outside, row_object, object_row, status
+
+    # ------------------------------------------------------------------ (3)+(4)
+    def object_features(self, b: SceneBatch, tables, use_visibility: bool, use_similarity: bool, sim_kernel):
+        """Returns (fused [sum Q, C] f32, weight_obj [wobj layout] f32)."""
+        counts, _, row_object, object_row, _ = tables
+        dim = int(b.feats.shape[1])
+        max_q = max(b.n_queries)
+        total_wobj = int(b.off_host["wobj"][-1])
+        weight = torch.zeros(max(total_wobj, 1), dtype=torch.float32, device=b.device)
+        sims, ld = None, 0
+        kern = SIM_KERNELS[sim_kernel] if use_similarity else _lib.DC_SIM_NONE
+        if use_similarity:
+            ld = self.lib.dc_view_score_ld(max_q)
+            sims = torch.empty((max(b.total_rows, 1), ld), dtype=torch.float32, device=b.device)
+            fdt = _lib.torch_dtype_code(b.feats.dtype)
+            ws_bytes = self.lib.dc_view_score_workspace(b.total_rows, b.total_queries, dim, fdt)
+            ws = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=b.device)
+            shift = (-ws.data_ptr()) % 1024
+            ws = ws[shift:shift + ws_bytes]
+            with self._tick("view_score"):
+                check(self.lib.dc_view_score(ptr(b.feats), fdt, b.total_rows, dim, ptr(b.off["feat"]), ptr(b.off["view"]),
+                                             ptr(b.queries), ptr(b.off["query"]), b.total_queries, b.n_scenes, max_q,
+                                             ptr(sims), ld, ptr(ws), ws_bytes, current_stream()))
+            self.launches += 4
+        check(self.lib.dc_view_weights(ptr(sims), ld, ptr(b.off["feat"]), ptr(b.off["view_scene"]), ptr(b.off["view"]),
+                                       ptr(b.off["query"]), ptr(b.off["wobj"]), ptr(row_object), ptr(counts), MAX_BINS,
+                                       b.total_views, kern, int(bool(use_visibility)), ptr(weight), current_stream()))
+        fused = torch.empty((b.total_queries, dim), dtype=torch.float32, device=b.device)
+        with self._tick("segmented_wmean"):
+            check(self.lib.dc_segmented_wmean(ptr(b.feats), _lib.torch_dtype_code(b.feats.dtype), dim, ptr(object_row),
+                                              ptr(weight), ptr(b.off["view"]), ptr(b.off["query"]), ptr(b.off["wobj"]),
+                                              b.n_scenes, max_q, ptr(fused), current_stream()))
+        self.launches += 2
+        return fused, weight
+
+    def scatter_to_points(self, b: SceneBatch, fused, labels, point_off, n_scenes, max_points, skip_first=True):
+        dim = int(fused.shape[1])
+        out = torch.empty((int(labels.shape[0]), dim), dtype=torch.float32, device=fused.device)
+        check(self.lib.dc_scatter_to_points(ptr(fused), ptr(b.off["query"]), ptr(labels), ptr(point_off), n_scenes,
+                                            max_points, dim, int(skip_first), ptr(out), current_stream()))
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ compaction
+    def compact(self, b: SceneBatch, any_vis, mask, extra_rows: Sequence[torch.Tensor] = ()):
+        """Drops never-visible points. Returns (new_index, kept_off (device), compacted mask, compacted rows)."""
+        n = b.total_points
+        new_index = torch.empty(max(n, 1), dtype=torch.int64, device=b.device)
+        kept_off = torch.empty(b.n_scenes + 1, dtype=torch.int64, device=b.device)
+        ws_bytes = self.lib.dc_compact_workspace(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=b.device)
+        check(self.lib.dc_compact_scan(ptr(any_vis), n, ptr(b.off["point"]), b.n_scenes, ptr(new_index), ptr(kept_off),
+                                       ptr(ws), ws_bytes, current_stream()))
+        self.launches += 4
+        kept_host = kept_off.cpu().numpy()  # sizes of the outputs: one small D2H, like the reference's .cpu() at :278
+        n_kept = np.diff(kept_host)
+        out_off_host = _prefix([v * k for v, k in zip(b.n_views, n_kept)])
+        out_off = torch.from_numpy(out_off_host).to(b.device)
+        cmask = torch.empty(int(out_off_host[-1]), dtype=mask.dtype, device=b.device)
+        check(self.lib.dc_compact_mask(ptr(mask), mask.element_size(), ptr(b.off["mask"]), ptr(b.off["point"]),
+                                       ptr(b.off["view"]), ptr(any_vis), ptr(new_index), ptr(kept_off), ptr(out_off),
+                                       b.n_scenes, max(b.n_points, default=0), max(b.n_views, default=0), ptr(cmask),
+                                       current_stream()))
+        self.launches += 1
+        rows_out = []
+        for t in extra_rows:
+            t2 = t.reshape(n, -1)
+            o = torch.empty((int(kept_host[-1]), t2.shape[1]), dtype=t.dtype, device=b.device)
+            check(self.lib.dc_compact_rows(ptr(t2), t2.shape[1] * t2.element_size(), ptr(any_vis), ptr(new_index), n,
+                                           ptr(o), current_stream()))
+            self.launches += 1
+            rows_out.append(o)
+        return new_index, kept_off, kept_host, out_off_host, cmask, rows_out
+
+    # ------------------------------------------------------------------ whole object-level pass
+    def fuse_object_level(self, b: SceneBatch, threshold=0.05, use_visibility=False, use_similarity=True,
+                          sim_kernel="max", mask_dtype=torch.uint8):
+        """Device-resident hot path of fuse_obj_prior (utils/feature_fusion.py:272-335) for a batch:
+        visibility -> instance tables -> view scores -> weights -> segmented weighted mean."""
+        mask, any_vis, _ = self.visibility(b, threshold, mask_dtype)
+        tables = self.seg_tables(b)
+        fused, weight = self.object_features(b, tables, use_visibility, use_similarity, sim_kernel)
+        return {"mask": mask, "any_visible": any_vis, "fused": fused, "weight_obj": weight, "view_status": tables[4]}
+
+    # ------------------------------------------------------------------ pixel-level path
+    def pixel_fuse(self, b: SceneBatch, mask_u8, sim_kernel, norm_feat: bool):
+        """aggregate_features (utils/feature_fusion.py:138-250): returns (sum_features [sum N, C] f32,
+        similarity weights [mask layout] f32 | None). `b.feats` is the (TV, ph, pw, C) patch stack."""
+        tv, ph, pw, dim = b.feats.shape
+        sums = torch.empty((b.total_points, dim), dtype=torch.float32, device=b.device)
+        kern = SIM_KERNELS[sim_kernel]
+        weight = torch.empty(int(b.off_host["mask"][-1]), dtype=torch.float32, device=b.device) \
+            if kern != _lib.DC_SIM_NONE else None
+        segs = b.segs if kern != _lib.DC_SIM_NONE else None
+        check(self.lib.dc_pixel_fuse(
+            ptr(b.points), ptr(b.off["point"]), ptr(b.off["view"]), ptr(b.inv_poses), ptr(b.intrinsics), ptr(b.off["mask"]),
+            ptr(mask_u8), ptr(segs), _lib.torch_dtype_code(segs.dtype) if segs is not None else _lib.DC_I64,
+            ptr(b.feats), int(ph), int(pw), int(dim), ptr(b.queries) if kern else None,
+            ptr(b.off["query"]) if kern else None, kern, int(bool(norm_feat)), b.n_scenes, max(b.n_points, default=0),
+            max(b.n_views, default=0), b.height, b.width, ptr(sums), ptr(weight), current_stream()))
+        self.launches += 1
+        return sums, weight
+
+    def pixel_normalize(self, b: SceneBatch, sums, mask_u8, weight):
+        check(self.lib.dc_pixel_normalize(ptr(sums), ptr(b.off["point"]), ptr(b.off["view"]), ptr(b.off["mask"]),
+                                          ptr(mask_u8), ptr(weight), b.n_scenes, max(b.n_points, default=0),
+                                          int(sums.shape[1]), current_stream()))
+        self.launches += 1
+        return sums
+
+    # ------------------------------------------------------------------ (6) grounding
+    def ground(self, feats: torch.Tensor, text: torch.Tensor, mode: int, softmax_temp: float = 0.1,
+               normalize: bool = True):
+        """feats (N,C) fp16/fp32 CUDA tensor (normalised IN PLACE when `normalize`), text (P,C) already
+        normalised prompt embeddings, prompt 0 positive. Returns (out, pred|None, minmax[4])."""
+        n, dim = feats.shape
+        p = int(text.shape[0])
+        dev = feats.device
+        is_f32 = feats.dtype == torch.float32
+        code = _lib.torch_dtype_code(feats.dtype)
+        if is_f32:
+            planes = torch.empty((2, max(n, 1), dim), dtype=torch.float16, device=dev)
+            x_hi, x_lo = planes[0], planes[1]
+            check(self.lib.dc_row_normalize(ptr(feats), code, n, dim, int(normalize), ptr(x_hi), ptr(x_lo), current_stream()))
+        else:
+            if normalize:
+                check(self.lib.dc_row_normalize(ptr(feats), code, n, dim, 1, None, None, current_stream()))
+            x_hi, x_lo = feats, None
+        t32 = text.to(torch.float32).contiguous()
+        tplanes = torch.empty((2, p, dim), dtype=torch.float16, device=dev)
+        t_lo = tplanes[1] if text.dtype == torch.float32 else None
+        check(self.lib.dc_row_normalize(ptr(t32), _lib.DC_F32, p, dim, 0, ptr(tplanes[0]), ptr(tplanes[1]), current_stream()))
+        minmax = torch.empty(4, dtype=torch.float32, device=dev)
+        check(self.lib.dc_ground_init_minmax(ptr(minmax), current_stream()))
+        pred = None
+        if mode == _lib.DC_GROUND_RAW:
+            out = torch.empty((n, p), dtype=torch.float32, device=dev)
+            ld = p
+        else:
+            out = torch.empty(n, dtype=torch.float32, device=dev)
+            ld = 1
+            if mode == _lib.DC_GROUND_ARGMAX:
+                pred = torch.empty(n, dtype=torch.uint8, device=dev)
+        check(self.lib.dc_ground(ptr(x_hi), ptr(x_lo), n, ptr(tplanes[0]), ptr(t_lo), p, dim, mode, float(softmax_temp),
+                                 ptr(out), ld, ptr(pred), ptr(minmax), current_stream()))
+        self.launches += 4
+        return out, pred, minmax
+
+    def minmax_threshold(self, values, minmax, use_raw: bool, threshold: float, want_pred: bool):
+        pred = torch.empty(values.numel(), dtype=torch.uint8, device=values.device) if want_pred else None
+        check(self.lib.dc_minmax_threshold(ptr(values), values.numel(), ptr(minmax), int(use_raw), float(threshold),
+                                           int(want_pred), ptr(pred), current_stream()))
+        self.launches += 1
+        return pred
+
+    # ------------------------------------------------------------------ (5) voxelisation
+    def voxelize(self, xyz: torch.Tensor, sample_off: torch.Tensor, voxel_size: float, labels=None, ignore_label=-100):
+        """Batch sparse_quantize. xyz (sum N,3) fp32, sample_off (B+1) int64 device.
+        Returns dict(coords, unique_map, inverse_map, voxel_labels, voxel_off) in the C-ABI layout."""
+        total = int(xyz.shape[0])
+        nb = int(sample_off.numel()) - 1
+        dev = xyz.device
+        coords = torch.empty((max(total, 1), 3), dtype=torch.int32, device=dev)
+        umap = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+        imap = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+        vlab = torch.empty(max(total, 1), dtype=torch.int32, device=dev) if labels is not None else None
+        voff = torch.empty(nb + 1, dtype=torch.int64, device=dev)
+        ws_bytes = self.lib.dc_voxelize_workspace(total)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(self.lib.dc_voxelize(ptr(xyz), ptr(sample_off), nb, total, float(voxel_size), ptr(labels), int(ignore_label),
+                                   ptr(coords), ptr(umap), ptr(imap), ptr(vlab), ptr(voff), ptr(ws), ws_bytes,
+                                   current_stream()))
+        self.launches += 10
+        return {"coords": coords, "unique_map": umap, "inverse_map": imap, "voxel_labels": vlab, "voxel_off": voff}
+
+    def voxel_gather(self, rows: torch.Tensor, sample_off, vox, n_voxels_total: int):
+        rows = rows.contiguous()
+        width = int(rows.shape[1])
+        out = torch.empty((n_voxels_total, width), dtype=rows.dtype, device=rows.device)
+        check(self.lib.dc_voxel_gather(ptr(rows), width * rows.element_size(), ptr(sample_off), ptr(vox["voxel_off"]),
+                                       ptr(vox["unique_map"]), int(sample_off.numel()) - 1, int(rows.shape[0]), ptr(out),
+                                       current_stream()))
+        self.launches += 1
+        return out

@@ -1,0 +1,269 @@
+/*
+ * libdropclip - C ABI of the B200-native DROP-CLIP fusion / grounding path.
+ *
+ * The reference (gtziafas/DROP-CLIP) is pure Python; it has no native boundary of its own.
+ * The drop-in boundary for callers is therefore the Python surface in `drop-clip_b200/`
+ * (same names and argument meaning as utils/feature_fusion.py, utils/projections.py and
+ * models/similarity.py). This header is the boundary *under* that surface: what the host
+ * side binds with ctypes, and what a maintainer of the reference would bind from
+ * utils/feature_fusion.py directly (INTEGRATION.md shows the stub). Each entry point names
+ * the reference lines it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its comment says "host";
+ *  - all memory is caller-owned; the library never allocates device memory, never
+ *    synchronises and only enqueues work on `stream` (a cudaStream_t);
+ *  - scene batches are ragged and described by prefix-offset arrays (CSR style), int64, on
+ *    the device; extents that size a launch are passed by value;
+ *  - return value: 0 on success, a negative dc_status otherwise; dc_last_error() gives a
+ *    thread-local message. No C++ exception crosses the boundary;
+ *  - built for sm_100a only; there is no CPU path. Calls fail with DC_ERR_CUDA on any other
+ *    device.
+ */
+#ifndef DROPCLIP_H_
+#define DROPCLIP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DC_ABI_VERSION 1
+#if defined(__GNUC__)
+#define DC_API __attribute__((visibility("default")))
+#else
+#define DC_API
+#endif
+
+typedef void* dc_stream_t; /* cudaStream_t */
+
+enum dc_status {
+  DC_OK = 0,
+  DC_ERR_INVALID = -1,     /* bad argument */
+  DC_ERR_CUDA = -2,        /* CUDA runtime / driver error, wrong architecture */
+  DC_ERR_UNSUPPORTED = -3, /* shape or dtype outside what the kernels implement */
+  DC_ERR_WORKSPACE = -4    /* workspace too small */
+};
+
+enum dc_dtype { DC_F16 = 0, DC_F32 = 1, DC_U8 = 2, DC_I32 = 3, DC_I64 = 4, DC_F64 = 5 };
+
+enum dc_sim_kernel { DC_SIM_NONE = 0, DC_SIM_MAX = 1, DC_SIM_MEAN = 2 };
+
+enum dc_ground_mode {
+  DC_GROUND_RAW = 0,    /* sims[n, p] = <x_n, t_p>                         models/similarity.py:49,67 */
+  DC_GROUND_PAIRED = 1, /* paired softmax of column 0 against the others   models/similarity.py:51-61 */
+  DC_GROUND_ARGMAX = 2  /* pos - mean(neg) and (argmax == 0)               models/similarity.py:91-101 */
+};
+
+DC_API int dc_abi_version(void);
+DC_API const char* dc_last_error(void);
+/* host out-params; any may be NULL */
+DC_API int dc_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * (1)+(2) Projection, depth-tolerance visibility and instance-mask lookup.
+ * Replaces MultiviewFeatureFusion.get_visibility_mask  utils/feature_fusion.py:81-125, the
+ * duplicate in aggregate_features :201-229, transform_pointcloud_to_camera_frame
+ * utils/transforms.py:52-61 and the `seg[ys, xs]` lookups tools/preprocess_data.py:395-401.
+ *
+ * For scene s, view v (global view index g = view_off[s] + v) and point i (global index
+ * j = point_off[s] + i) it evaluates, in fp64 with the exact operation order of the
+ * reference's BLAS calls (k-ascending fused multiply-add chains):
+ *     c  = inv_pose[g][:3,:] . [p;1];  c.y = -c.y;  c.z = -c.z;   q = K[s] . c
+ *     (u,v) = trunc(q.x / q.z, q.y / q.z)   (0,0) when q.z == 0
+ *     visible = 0<=u<W and 0<=v<H and |double(depth[g][v,u]) - q.z| <= threshold
+ * and writes mask[mask_off[s] + v*N_s + i] (uint8 or int64, selected by mask_elem_size).
+ * Optional outputs (NULL to skip): any_visible[j] = OR over views; point_object[same layout
+ * as mask] = seg[g][v,u] for visible points, -1 otherwise (needs `seg`).
+ * The inverse pose is an input (16 fp32 per view, row-major) because the reference inverts in
+ * fp32 with LAPACK on the host (np.linalg.inv, utils/transforms.py:54).
+ */
+DC_API int dc_project_visibility(const double* points, const int64_t* point_off, const int64_t* view_off,
+                          const float* depths, const float* inv_poses, const double* intrinsics,
+                          const int64_t* mask_off, int n_scenes, int64_t max_points_per_scene,
+                          int max_views_per_scene, int height, int width, double threshold,
+                          void* mask, int mask_elem_size, uint8_t* any_visible,
+                          const void* seg, int seg_dtype, int32_t* point_object, dc_stream_t stream);
+
+/* Per-view instance histogram: counts[g*nbins + id] = #pixels of view g with that id,
+ * outside[g] = #pixels whose id is not in [0,nbins). Replaces np.unique(seg)
+ * utils/feature_fusion.py:307 and (seg == obj).sum() :320. seg_dtype: DC_U8 / DC_I32 / DC_I64. */
+DC_API int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_views, int64_t pixels_per_view,
+                     int nbins, uint32_t* counts, uint32_t* outside, dc_stream_t stream);
+
+/* Binds feature rows to object ids the way the reference's loop does (utils/feature_fusion.py
+ * :307,315,333): the ids present in a view, ascending, minus the smallest one; row i of the
+ * view's feature block belongs to the i-th remaining id.
+ *   feat_off   [total_views+1] first feature row of each view
+ *   view_scene [total_views]   scene of each view;   view_off / query_off / wobj_off [n_scenes+1]
+ * Outputs: row_object[total_rows] (id or -1), object_row[wobj layout: wobj_off[s] + id*V_s + v]
+ * (global row or -1), view_status[total_views] bit0: an id outside [0,Q_s) is present (the
+ * reference raises IndexError), bit1: fewer feature rows than ids (IndexError as well). */
+DC_API int dc_view_table(const uint32_t* counts, const uint32_t* outside, const int64_t* feat_off,
+                  const int32_t* view_scene, const int64_t* view_off, const int64_t* query_off,
+                  const int64_t* wobj_off, int64_t total_views, int64_t total_rows, int64_t total_wobj,
+                  int nbins, int32_t* row_object, int32_t* object_row, int32_t* view_status,
+                  dc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) Semantic view-informativeness score. Replaces utils/feature_fusion.py:311-313:
+ *     sims[r, o] = < feat[r] / |feat[r]| , query[query_off[s] + o] >     r in view g of scene s
+ * as one batched tcgen05 GEMM (fp16 operand planes, fp32 accumulate in TMEM; fp32 inputs are
+ * split into hi+lo fp16 planes so the result keeps fp32-level accuracy).
+ * feats: [total_rows, dim] DC_F16 or DC_F32 (rows of all views stacked; dim % 64 == 0).
+ * queries: [total_queries, dim] fp32.  sims: [total_rows, sims_ld] fp32, sims_ld >= 16-aligned
+ * max Q_s (use dc_view_score_ld()).
+ * workspace: dc_view_score_workspace() bytes, 1024-byte aligned.
+ */
+DC_API int dc_view_score_ld(int max_queries_per_scene);
+DC_API size_t dc_view_score_workspace(int64_t total_rows, int64_t total_queries, int dim, int feat_dtype);
+DC_API int dc_view_score(const void* feats, int feat_dtype, int64_t total_rows, int dim, const int64_t* feat_off,
+                  const int64_t* view_off, const float* queries, const int64_t* query_off,
+                  int64_t total_queries, int n_scenes, int max_queries_per_scene, float* sims, int sims_ld,
+                  void* workspace, size_t workspace_bytes, dc_stream_t stream);
+
+/* View weights. Replaces utils/feature_fusion.py:313-331 and calculate_sim :65-73: per view a
+ * global min-max normalisation of its sims block, then per bound row
+ *     w = clip(sn[obj] - max_{o != obj} sn[o], 1e-6)        (DC_SIM_MAX, or mean for DC_SIM_MEAN)
+ * use_visibility writes the pixel count of the object instead; DC_SIM_NONE without visibility
+ * writes 1. Similarity overrides visibility like the reference (quirk q8).
+ * weight_obj: wobj layout, fp32, must be zero-filled by the caller. */
+DC_API int dc_view_weights(const float* sims, int sims_ld, const int64_t* feat_off, const int32_t* view_scene,
+                    const int64_t* view_off, const int64_t* query_off, const int64_t* wobj_off,
+                    const int32_t* row_object, const uint32_t* counts, int nbins, int64_t total_views,
+                    int sim_kernel, int use_visibility, float* weight_obj, dc_stream_t stream);
+
+/* (4) Object-level segmented weighted mean over views. Replaces the einsum and division at
+ * utils/feature_fusion.py:333-335:  fused[query_off[s]+o, :] = sum_v w[o,v] * feat[row(o,v)] / sum_v w[o,v]
+ * (0/0 = NaN for objects seen in no view, quirk q10). fused: [total_queries, dim] fp32. */
+DC_API int dc_segmented_wmean(const void* feats, int feat_dtype, int dim, const int32_t* object_row,
+                       const float* weight_obj, const int64_t* view_off, const int64_t* query_off,
+                       const int64_t* wobj_off, int n_scenes, int max_queries_per_scene, float* fused,
+                       dc_stream_t stream);
+
+/* (4) Scatter object features back to points. Replaces reconstruct_per_obj_feat
+ * utils/feature_fusion.py:127-136 (skip_first = 1: object 0 and unknown labels give zero rows)
+ * and the dataset twin feat[label] data/dataset_blender.py:128-130 (skip_first = 0).
+ * labels: [total_points] int64; out: [total_points, dim] fp32. */
+DC_API int dc_scatter_to_points(const float* fused, const int64_t* query_off, const int64_t* labels,
+                         const int64_t* point_off, int n_scenes, int64_t max_points_per_scene, int dim,
+                         int skip_first, float* out, dc_stream_t stream);
+
+/* Stream compaction of never-visible points (utils/feature_fusion.py:277-281, :257-264).
+ * new_index[j] = rank of point j among the kept points of the whole batch (exclusive scan of
+ * any_visible), kept_off[n_scenes+1] = scene prefix of kept counts. workspace:
+ * dc_compact_workspace(total_points) bytes. */
+DC_API size_t dc_compact_workspace(int64_t total_points);
+DC_API int dc_compact_scan(const uint8_t* any_visible, int64_t total_points, const int64_t* point_off,
+                    int n_scenes, int64_t* new_index, int64_t* kept_off, void* workspace,
+                    size_t workspace_bytes, dc_stream_t stream);
+/* out[new_index[j]] = in[j] for kept rows of `row_bytes` bytes (points, colours, labels, features). */
+DC_API int dc_compact_rows(const void* in, int64_t row_bytes, const uint8_t* any_visible, const int64_t* new_index,
+                    int64_t total_points, void* out, dc_stream_t stream);
+/* Column compaction of the per-scene (V_s, N_s) masks into (V_s, N'_s) blocks at out_off[s]
+ * (out_off = prefix of V_s * N'_s, computed by the caller from kept_off). elem_size 1, 4 or 8. */
+DC_API int dc_compact_mask(const void* mask, int elem_size, const int64_t* mask_off, const int64_t* point_off,
+                    const int64_t* view_off, const uint8_t* any_visible, const int64_t* new_index,
+                    const int64_t* kept_off, const int64_t* out_off, int n_scenes,
+                    int64_t max_points_per_scene, int max_views_per_scene, void* out, dc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pixel-level fusion. Replaces aggregate_features utils/feature_fusion.py:138-250 and the
+ * division in fuse_points :266-268 without materialising the 480x640xC bicubic map: for each
+ * visible (point, view) it evaluates the 16 bicubic taps (align_corners=False, A=-0.75) of the
+ * patch map at the projected pixel, optionally L2-normalises, scores the feature against all
+ * queries to obtain the relative-similarity weight of the pixel's instance id, and accumulates
+ * point-major over views.
+ *   patch_feats [total_views, ph, pw, dim] fp32;  queries as above (sim_kernel != NONE)
+ *   visible     [mask layout] uint8 from dc_project_visibility; pixels recomputed internally
+ *   out_sum     [total_points, dim] fp32 (sum of weighted features, = sum_features :243)
+ *   out_weight  [mask layout] fp32 similarity weights (similarity_mask :238) or NULL
+ */
+DC_API int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t* view_off,
+                  const float* inv_poses, const double* intrinsics, const int64_t* mask_off,
+                  const uint8_t* visible, const void* seg, int seg_dtype, const float* patch_feats, int patch_h,
+                  int patch_w, int dim, const float* queries, const int64_t* query_off, int sim_kernel,
+                  int norm_feat, int n_scenes, int64_t max_points_per_scene, int max_views_per_scene,
+                  int height, int width, float* out_sum, float* out_weight, dc_stream_t stream);
+/* feat[j,:] = sum[j,:] / denom[j] with denom = sum_v weight (similarity) or sum_v visible. */
+DC_API int dc_pixel_normalize(float* sums, const int64_t* point_off, const int64_t* view_off, const int64_t* mask_off,
+                       const uint8_t* visible, const float* weight, int n_scenes, int64_t max_points_per_scene,
+                       int dim, dc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (5) Voxelisation to MinkowskiEngine sparse coordinates. Replaces ME.utils.sparse_quantize as
+ * called at data/dataset_blender.py:406-414 / data/dataset.py:164-172, for a batch of samples:
+ *   coords = floor(xyz / voxel_size) (fp32 true division) -> int32; unique voxels in order of
+ *   first occurrence per sample; inverse map; label collision -> ignore_label.
+ *   xyz [total_points,3] fp32, sample_off [n_samples+1], labels int32 or NULL.
+ * Outputs: coords [total_points,3] int32 (first n_voxels rows valid per sample block),
+ *   unique_map [total_points] int64 (sample-local point index of each voxel), inverse_map
+ *   [total_points] int64 (sample-local voxel index of each point), voxel_labels int32 or NULL,
+ *   voxel_off [n_samples+1] prefix of voxel counts. Sample blocks in coords/unique_map/
+ *   voxel_labels start at sample_off[b] (not compacted across samples; use voxel_off for counts).
+ */
+DC_API size_t dc_voxelize_workspace(int64_t total_points);
+DC_API int dc_voxelize(const float* xyz, const int64_t* sample_off, int n_samples, int64_t total_points,
+                float voxel_size, const int32_t* labels, int32_t ignore_label, int32_t* coords,
+                int64_t* unique_map, int64_t* inverse_map, int32_t* voxel_labels, int64_t* voxel_off,
+                void* workspace, size_t workspace_bytes, dc_stream_t stream);
+/* out[b-th sample voxel k, :] = in[sample_off[b] + unique_map[sample_off[b] + k], :] - the
+ * features[unique_map] gather of sparse_quantize; rows of `row_bytes` bytes, output compacted
+ * with voxel_off. */
+DC_API int dc_voxel_gather(const void* in, int64_t row_bytes, const int64_t* sample_off, const int64_t* voxel_off,
+                    const int64_t* unique_map, int n_samples, int64_t total_points, void* out,
+                    dc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (6) Text-prompt grounding. Replaces ClipSimilarity.compute_similarity / predict
+ * models/similarity.py:28-101 (after the text tower) and _get_similarity engine/distil.py:244-246.
+ */
+/* In-place row L2 normalisation x /= |x| with torch's per-dtype rounding (fp16: the norm and
+ * the quotient are rounded to fp16). models/similarity.py:35,45,77. Optionally also writes
+ * fp16 hi/lo operand planes for the GEMM (NULL to skip; lo only meaningful for fp32 input). */
+DC_API int dc_row_normalize(void* x, int dtype, int64_t n_rows, int dim, int normalize, void* plane_hi,
+                     void* plane_lo, dc_stream_t stream);
+
+/* sims = X . T^T followed by the mode's epilogue, one tcgen05 GEMM.
+ *   x_hi/x_lo  [n_points, dim] fp16 planes (x_lo NULL for fp16 features)
+ *   t_hi/t_lo  [n_prompts, dim] fp16 planes, n_prompts <= 256, prompt 0 is the positive one
+ *   DC_GROUND_RAW:    out [n_points, out_ld] fp32 raw similarities
+ *   DC_GROUND_PAIRED: out [n_points] fp32
+ *   DC_GROUND_ARGMAX: out [n_points] fp32 (pos - mean(neg)), pred [n_points] uint8 (argmax == 0)
+ *   minmax [4] fp32: min/max of `out` values and min/max of the raw similarities (device,
+ *   updated atomically; initialise with dc_ground_init_minmax).
+ */
+DC_API int dc_ground_init_minmax(float* minmax, dc_stream_t stream);
+DC_API int dc_ground(const void* x_hi, const void* x_lo, int64_t n_points, const void* t_hi, const void* t_lo,
+              int n_prompts, int dim, int mode, float softmax_temp, float* out, int out_ld, uint8_t* pred,
+              float* minmax, dc_stream_t stream);
+/* Global min-max normalisation + threshold (models/similarity.py:83-88, :95-98):
+ * values <- (v - min)/(max - min) (or v / max when the raw extrema coincide), pred = values > thr
+ * when pred_from_threshold != 0. */
+DC_API int dc_minmax_threshold(float* values, int64_t n, const float* minmax, int use_raw_extrema_for_test,
+                        float threshold, int pred_from_threshold, uint8_t* pred, dc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Geometry helpers of utils/projections.py.
+ */
+/* depth_to_pointcloud utils/projections.py:67-86 (+ optional axis flips :89-97 and cam->world
+ * utils/transforms.py:43-49): out[v, y, x, :] fp64. flip_y/flip_z negate after back-projection;
+ * poses (fp32 [n_views,16], camera->world) may be NULL. */
+DC_API int dc_backproject(const float* depths, int n_views, int height, int width, const double* fxfycxcy,
+                   int flip_y, int flip_z, const float* poses, double* out, dc_stream_t stream);
+/* pointcloud_to_pixel utils/projections.py:59-64: un-truncated fp64 pixel coordinates. */
+DC_API int dc_points_to_pixels(const double* cam_points, int64_t n, const double* fxfycxcy, double* pixels,
+                        dc_stream_t stream);
+
+/* Rigid transform out[i,:] = (M . [p_i;1])[:3] in fp64 with np.dot's operation order;
+ * M: 16 fp32 (host pointer, row-major). Replaces transform_pointcloud_to_world_frame /
+ * _to_camera_frame utils/transforms.py:43-61 (the caller inverts the pose for the latter). */
+DC_API int dc_transform_points(const double* points, int64_t n, const float* matrix_host, double* out,
+                        dc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DROPCLIP_H_ */
