@@ -13,15 +13,21 @@
 // multiply-adds (see oracle/visibility_ref.c), spelled out below with __dmul_rn / __fma_rn so
 // that the compiler can neither contract nor re-associate anything.
 //
-// Roofline: HBM-bound by design - 24 B/point + (4 B depth sample + 1 or 8 B mask) per
-// (point, view); the fp64 work is ~35 DFMA-class instructions per (point, view).
+// Measured (profiles/r01_*): the kernel is NOT HBM-bound - the depth gathers hit L2 (~85 %) and
+// the fp64 pipe (2 cycles per warp instruction) plus issue slots set the pace. Three exact
+// rewrites therefore cut fp64 work without changing a single result bit (each is argued where it
+// is used): (a) the y/z sign flip is folded into pre-negated matrix rows, (b) structural zeros of
+// a pinhole K are skipped for finite operands, (c) the two IEEE divisions share one refined
+// reciprocal, whose quotients are only trusted when they are provably far from every integer;
+// otherwise the thread falls back to the literal evaluation.
 #include "common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kPointsPerThread = 4;
+constexpr int kPointsPerThread = 2;
 constexpr int kPointsPerBlock = kThreads * kPointsPerThread;
+constexpr double kBig = 1e100;  // operands below this magnitude cannot overflow anywhere in the chain
 
 struct VisParams {
   const double* points;
@@ -46,9 +52,63 @@ __device__ __forceinline__ int load_seg(const void* seg, int dtype, int64_t idx)
   return (int)__ldg(reinterpret_cast<const long long*>(seg) + idx);
 }
 
+__device__ __forceinline__ double rcp_refined(double x) {
+  // rcp.approx.ftz.f64 carries ~20 mantissa bits; two Newton steps take the relative error to a
+  // few 2^-53. Only used for |x| in (1e-200, 1e200), where neither x nor 1/x is subnormal.
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = __fma_rn(-x, r, 1.0);
+  r = __fma_rn(r, e, r);
+  e = __fma_rn(-x, r, 1.0);
+  r = __fma_rn(r, e, r);
+  return r;
+}
+
+// Literal evaluation of one (point, view): the operation sequence of the reference
+// (oracle/visibility_ref.c), every structural zero of K multiplied out so that non-finite operands
+// propagate exactly as in numpy. `m` holds the inverse pose with rows 1 and 2 pre-negated, see (a).
+__device__ __noinline__ bool literal_pixel(const double* __restrict__ m, const double* __restrict__ K, double x, double y,
+                                           double z, int width, int height, int& pix, double& qz_out) {
+  const double cx = __dadd_rn(m[3], __fma_rn(m[2], z, __fma_rn(m[1], y, __dmul_rn(m[0], x))));
+  const double cy = __dadd_rn(m[7], __fma_rn(m[6], z, __fma_rn(m[5], y, __dmul_rn(m[4], x))));
+  const double cz = __dadd_rn(m[11], __fma_rn(m[10], z, __fma_rn(m[9], y, __dmul_rn(m[8], x))));
+  const double qx = __fma_rn(K[2], cz, __fma_rn(K[1], cy, __dmul_rn(K[0], cx)));
+  const double qy = __fma_rn(K[5], cz, __fma_rn(K[4], cy, __dmul_rn(K[3], cx)));
+  const double qz = __fma_rn(K[8], cz, __fma_rn(K[7], cy, __dmul_rn(K[6], cx)));
+  qz_out = qz;
+  int pu = 0, pv = 0;
+  bool in = true;
+  if (qz != 0.0) {
+    const double uq = __ddiv_rn(qx, qz);
+    const double vq = __ddiv_rn(qy, qz);
+    // numpy truncates toward zero into int64, then tests 0 <= . < limit  <=>  -1 < q < limit; NaN/inf fail
+    in = (uq > -1.0) && (uq < (double)width) && (vq > -1.0) && (vq < (double)height);
+    if (in) {
+      pu = (int)uq;
+      pv = (int)vq;
+    }
+  }
+  pix = pv * width + pu;
+  return in;
+}
+
+// Classifies an approximate quotient q (relative error <= 2^-50) against [0, limit) under
+// truncation toward zero. Returns 0 = surely outside, 1 = surely inside (pixel in `out`),
+// 2 = too close to an integer (or too large) to decide without the exact quotient.
+__device__ __forceinline__ int classify(double q, int limit, int& out) {
+  const int i = __double2int_rz(q);  // saturating
+  const double d = q - (double)i;    // in (-1, 1) unless saturated
+  // |q| <= 1e6 bounds the absolute error by 1e6 * 2^-50 < 1e-9; |d| in (1e-8, 1 - 1e-8) then means no
+  // integer lies between q and the correctly rounded exact quotient, so both truncate to i.
+  if (!(fabs(fabs(d) - 0.5) < 0.5 - 1e-8) || !(fabs(q) <= 1.0e6)) return 2;
+  out = i;
+  return ((unsigned)i < (unsigned)limit) ? 1 : 0;
+}
+
 template <typename MaskT>
-__global__ void __launch_bounds__(kThreads) project_visibility_kernel(VisParams p) {
-  extern __shared__ double s_cam[];  // [n_views][12] inverse pose rows (fp64) then [9] intrinsics
+__global__ void __launch_bounds__(kThreads, 4) project_visibility_kernel(VisParams p) {
+  extern __shared__ double s_cam[];  // [n_views][12] inverse pose rows (fp64), rows 1,2 negated; then [9] K
+  __shared__ int s_ok;
   const int scene = blockIdx.y;
   const int64_t p0 = p.point_off[scene];
   const int64_t n_pts = p.point_off[scene + 1] - p0;
@@ -57,17 +117,32 @@ __global__ void __launch_bounds__(kThreads) project_visibility_kernel(VisParams 
   const int64_t v0 = p.view_off[scene];
   const int n_views = (int)(p.view_off[scene + 1] - v0);
 
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  bool mine_ok = true;
   for (int i = threadIdx.x; i < n_views * 12; i += kThreads) {
     const int v = i / 12, e = i - v * 12;
-    s_cam[i] = (double)__ldg(p.inv_poses + (v0 + v) * 16 + e);  // fp32 -> fp64 like np.dot's upcast
+    const double val = (double)__ldg(p.inv_poses + (v0 + v) * 16 + e);  // fp32 -> fp64 like np.dot's upcast
+    mine_ok &= fabs(val) < kBig;
+    // (a) round-to-nearest is sign-symmetric, so evaluating the chain with rows 1 and 2 negated gives
+    //     exactly the negated camera-frame y and z (only the sign of an exact zero can differ, which
+    //     no later step observes).
+    s_cam[i] = (e >= 4) ? -val : val;
   }
   double* s_K = s_cam + n_views * 12;
-  if (threadIdx.x < 9) s_K[threadIdx.x] = __ldg(p.intrinsics + (int64_t)scene * 9 + threadIdx.x);
+  if (threadIdx.x < 9) {
+    const double kv = __ldg(p.intrinsics + (int64_t)scene * 9 + threadIdx.x);
+    s_K[threadIdx.x] = kv;
+    mine_ok &= fabs(kv) < kBig;
+  }
+  if (!mine_ok) s_ok = 0;
   __syncthreads();
+  const double K0 = s_K[0], K2 = s_K[2], K4 = s_K[4], K5 = s_K[5];
+  // (b) pinhole structure K = [[fx,0,cx],[0,fy,cy],[0,0,1]], every matrix entry finite and < 1e100
+  const bool pinhole = s_ok && s_K[1] == 0.0 && s_K[3] == 0.0 && s_K[6] == 0.0 && s_K[7] == 0.0 && s_K[8] == 1.0;
 
   double px[kPointsPerThread], py[kPointsPerThread], pz[kPointsPerThread];
-  bool valid[kPointsPerThread];
-  bool any[kPointsPerThread];
+  bool valid[kPointsPerThread], fast[kPointsPerThread], any[kPointsPerThread];
 #pragma unroll
   for (int k = 0; k < kPointsPerThread; ++k) {
     const int64_t i = tile0 + k * kThreads + threadIdx.x;
@@ -77,66 +152,70 @@ __global__ void __launch_bounds__(kThreads) project_visibility_kernel(VisParams 
     px[k] = __ldg(p.points + 3 * j);
     py[k] = __ldg(p.points + 3 * j + 1);
     pz[k] = __ldg(p.points + 3 * j + 2);
+    fast[k] = pinhole && fabs(px[k]) < kBig && fabs(py[k]) < kBig && fabs(pz[k]) < kBig;  // NaN -> false
   }
 
-  const double K0 = s_K[0], K1 = s_K[1], K2 = s_K[2], K3 = s_K[3], K4 = s_K[4], K5 = s_K[5], K6 = s_K[6],
-               K7 = s_K[7], K8 = s_K[8];
-  const double w_lim = (double)p.width, h_lim = (double)p.height;
   const int64_t hw = (int64_t)p.height * p.width;
   MaskT* mask_scene = reinterpret_cast<MaskT*>(p.mask) + p.mask_off[scene];
   int32_t* pobj_scene = p.point_object ? p.point_object + p.mask_off[scene] : nullptr;
 
   for (int v = 0; v < n_views; ++v) {
     const double* m = s_cam + v * 12;
-    const double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5], m6 = m[6], m7 = m[7],
-                 m8 = m[8], m9 = m[9], m10 = m[10], m11 = m[11];
     const float* depth = p.depths + (v0 + v) * hw;
-    bool vis[kPointsPerThread];
-    int64_t pix[kPointsPerThread];
-    double qz[kPointsPerThread];
     bool inside[kPointsPerThread];
+    int pix[kPointsPerThread];
+    double qz[kPointsPerThread];
 #pragma unroll
     for (int k = 0; k < kPointsPerThread; ++k) {
-      // dgemm(inv_pose, [p;1]): acc = a0*b0; acc = fma(a1,b1,acc); ...; last term is a3*1
-      double cx = __dadd_rn(m3, __fma_rn(m2, pz[k], __fma_rn(m1, py[k], __dmul_rn(m0, px[k]))));
-      double cy = __dadd_rn(m7, __fma_rn(m6, pz[k], __fma_rn(m5, py[k], __dmul_rn(m4, px[k]))));
-      double cz = __dadd_rn(m11, __fma_rn(m10, pz[k], __fma_rn(m9, py[k], __dmul_rn(m8, px[k]))));
-      cy = -cy;
-      cz = -cz;
-      // K @ c (structural zeros of K are kept so that non-finite inputs behave identically)
-      const double qx = __fma_rn(K2, cz, __fma_rn(K1, cy, __dmul_rn(K0, cx)));
-      const double qy = __fma_rn(K5, cz, __fma_rn(K4, cy, __dmul_rn(K3, cx)));
-      qz[k] = __fma_rn(K8, cz, __fma_rn(K7, cy, __dmul_rn(K6, cx)));
-      int pu = 0, pv = 0;
-      bool in = true;
-      if (qz[k] != 0.0) {
-        const double uq = __ddiv_rn(qx, qz[k]);
-        const double vq = __ddiv_rn(qy, qz[k]);
-        // trunc-toward-zero into int64 then 0 <= . < limit  <=>  -1 < q < limit ; NaN/inf fail
-        in = (uq > -1.0) && (uq < w_lim) && (vq > -1.0) && (vq < h_lim);
-        if (in) {
-          pu = (int)uq;
-          pv = (int)vq;
+      bool literal = !fast[k];
+      inside[k] = false;
+      pix[k] = 0;
+      qz[k] = 0.0;
+      if (fast[k]) {
+        // dgemm(inv_pose, [p;1]): acc = a0*b0; acc = fma(a1,b1,acc); acc = fma(a2,b2,acc); acc += a3*1
+        const double cx = __dadd_rn(m[3], __fma_rn(m[2], pz[k], __fma_rn(m[1], py[k], __dmul_rn(m[0], px[k]))));
+        const double cy = __dadd_rn(m[7], __fma_rn(m[6], pz[k], __fma_rn(m[5], py[k], __dmul_rn(m[4], px[k]))));
+        const double cz = __dadd_rn(m[11], __fma_rn(m[10], pz[k], __fma_rn(m[9], py[k], __dmul_rn(m[8], px[k]))));
+        // (b) all operands are finite here, so fma(0, cy, acc) == acc, fma(fy, cy, 0*cx) == fy*cy and
+        //     fma(1, cz, 0) == cz up to the sign of an exact zero.
+        const double qx = __fma_rn(K2, cz, __dmul_rn(K0, cx));
+        const double qy = __fma_rn(K5, cz, __dmul_rn(K4, cy));
+        qz[k] = cz;
+        const double aqz = fabs(cz);
+        if (cz == 0.0) {
+          inside[k] = true;  // the reference skips the division: pixel (0,0)
+        } else if (aqz > 1e-200 && aqz < 1e200) {
+          // (c) one refined reciprocal serves both quotients; see classify() for when it is trusted
+          const double r = rcp_refined(cz);
+          int pu = 0, pv = 0;
+          const int su = classify(__dmul_rn(qx, r), p.width, pu);
+          const int sv = classify(__dmul_rn(qy, r), p.height, pv);
+          if (su == 1 && sv == 1) {
+            inside[k] = true;
+            pix[k] = pv * p.width + pu;
+          } else if (su != 0 && sv != 0) {
+            literal = true;  // undecided in some axis and not surely outside in the other
+          }
+        } else {
+          literal = true;
         }
       }
-      inside[k] = in && valid[k];
-      pix[k] = (int64_t)pv * p.width + pu;
+      if (literal) inside[k] = literal_pixel(m, s_K, px[k], py[k], pz[k], p.width, p.height, pix[k], qz[k]);
+      inside[k] = inside[k] && valid[k];
     }
     float sensor[kPointsPerThread];
 #pragma unroll
     for (int k = 0; k < kPointsPerThread; ++k) sensor[k] = inside[k] ? __ldg(depth + pix[k]) : 0.f;
-#pragma unroll
-    for (int k = 0; k < kPointsPerThread; ++k) {
-      vis[k] = inside[k] && (fabs((double)sensor[k] - qz[k]) <= p.threshold);
-      any[k] |= vis[k];
-    }
     const int64_t row = (int64_t)v * n_pts + tile0 + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < kPointsPerThread; ++k) {
+      // torch: abs(fp32 depth promoted to fp64 - z') <= threshold, compared in fp64
+      const bool vis = inside[k] && (fabs((double)sensor[k] - qz[k]) <= p.threshold);
+      any[k] |= vis;
       if (valid[k]) {
-        mask_scene[row + k * kThreads] = (MaskT)vis[k];
+        mask_scene[row + k * kThreads] = (MaskT)vis;
         if (pobj_scene)
-          pobj_scene[row + k * kThreads] = vis[k] ? load_seg(p.seg, p.seg_dtype, (v0 + v) * hw + pix[k]) : -1;
+          pobj_scene[row + k * kThreads] = vis ? load_seg(p.seg, p.seg_dtype, (v0 + v) * hw + pix[k]) : -1;
       }
     }
   }

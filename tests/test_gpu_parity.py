@@ -77,6 +77,54 @@ def test_visibility_and_object_lookup_vs_c_oracle_fresh_scene():
         assert np.array_equal(pobj[v].astype(np.int64), want_obj)
 
 
+def test_visibility_points_on_pixel_corners_take_the_exact_path():
+    """Points back-projected from integer pixel corners project to (almost) exact integers - the
+    case where the shared-reciprocal fast path must defer to the IEEE divisions."""
+    from oracle import c_oracle
+    from dropclip_b200.scenes import small_scene
+    from dropclip_b200.engine import intrinsic_matrix
+    sc = small_scene(99, n_views=5, n_points=100, n_objects=5, height=120, width=160)
+    H, W = 120, 160
+    rng = np.random.default_rng(9)
+    pts = []
+    for v in range(sc.n_views):
+        P = sc.camera_poses[v].astype(np.float64)
+        us = rng.integers(-1, W + 1, size=4000).astype(np.float64)
+        vs = rng.integers(-1, H + 1, size=4000).astype(np.float64)
+        us[::3] += rng.choice([-1e-13, 1e-13, 1e-10, -1e-9, 0.0], size=us[::3].shape)
+        z = sc.depths[v][np.clip(vs, 0, H - 1).astype(int), np.clip(us, 0, W - 1).astype(int)].astype(np.float64)
+        xc = (us - sc.intrinsic["cx"]) / sc.intrinsic["fx"] * z
+        yc = (vs - sc.intrinsic["cy"]) / sc.intrinsic["fy"] * z
+        pts.append(P[:3, 3] + xc[:, None] * P[:3, 0] - yc[:, None] * P[:3, 1] - z[:, None] * P[:3, 2])
+    pts = np.concatenate(pts)
+    sc.inv_poses = [np.linalg.inv(p) for p in sc.camera_poses]
+    m, _, _ = engine_visibility(sc, pts, torch.uint8)
+    want = c_oracle.visibility_mask(pts, sc.depths, None, intrinsic_matrix(sc.intrinsic), inv_poses=sc.inv_poses)
+    assert np.array_equal(m.astype(np.int64), want)
+    assert want.sum() > 1000
+
+
+def test_visibility_general_intrinsics_and_huge_values():
+    """Non-pinhole K (skew, non-unit K[2,2]) and operands >= 1e100 use the literal path."""
+    from oracle import c_oracle
+    from dropclip_b200 import _lib
+    from dropclip_b200.engine import FusionEngine, SceneBatch
+    from dropclip_b200.scenes import small_scene
+    sc = small_scene(98, n_views=3, n_points=3000, n_objects=5, height=120, width=160)
+    K = np.array([[110.0, 0.7, 79.5], [0.01, 111.0, 59.5], [1e-4, -2e-4, 1.01]])
+    pts = sc.points.copy()
+    pts[:5] *= 1e150
+    inv = [np.linalg.inv(p) for p in sc.camera_poses]
+    eng = FusionEngine("cuda")
+    b = SceneBatch.from_host([{"points": pts, "depths": sc.depths, "camera_poses": sc.camera_poses,
+                               "intrinsic": sc.intrinsic}], "cuda", inv_poses=[inv])
+    b.intrinsics = torch.from_numpy(K.reshape(1, 9)).cuda()
+    mask, _, _ = eng.visibility(b, 0.05, torch.uint8)
+    with np.errstate(all="ignore"):
+        want = c_oracle.visibility_mask(pts, sc.depths, None, K, inv_poses=inv)
+    assert np.array_equal(mask.view(3, -1).cpu().numpy().astype(np.int64), want)
+
+
 def test_get_visibility_mask_dropin_types():
     z = gio.load("fuse_s0.npz")
     sc = gio.scene_of(z)

@@ -1,0 +1,175 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, host-side layout
+logic, install aliasing, and the N>1 sharding/gather path on gloo with world_size 2."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "dropclip.h")).read()
+    return sorted(set(re.findall(r"^DC_API\s+[\w\s\*]+?\b(dc_\w+)\s*\(", text, flags=re.M)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from dropclip_b200 import _lib, build
+    lib_path = build.build()
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True, check=True).stdout
+    exported = sorted(set(re.findall(r"\sT\s+(dc_\w+)", out)))
+    declared = header_symbols()
+    assert len(declared) >= 28
+    assert exported == declared, (set(declared) ^ set(exported))
+    assert sorted(_lib.SIGNATURES) == declared
+    lib = _lib.load()
+    assert lib.dc_abi_version() == 1
+    assert lib.dc_last_error() is not None
+    # pure host queries only: no compute call without a GPU
+    assert lib.dc_view_score_ld(21) == 32 and lib.dc_view_score_ld(200) == 256
+    assert lib.dc_compact_workspace(100000) > 0 and lib.dc_voxelize_workspace(10000) > 0
+
+
+def test_library_targets_sm100a_with_tensor_core_and_tma_instructions():
+    from dropclip_b200 import build
+    sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from dropclip_b200.engine import FusionEngine
+    from dropclip_b200.feature_fusion import MultiviewFeatureFusion
+    with pytest.raises(RuntimeError):
+        FusionEngine("cuda")
+    M = MultiviewFeatureFusion({"fx": 1.0, "fy": 1.0, "cx": 0.0, "cy": 0.0}, use_similarity=False, device="cpu")
+    with pytest.raises(RuntimeError):
+        M.get_visibility_mask(np.zeros((3, 3)), [np.zeros((480, 640), np.float32)], [np.eye(4, dtype=np.float32)])
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "drop-clip_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_batch_offsets_layout():
+    from dropclip_b200.engine import SceneBatch
+    off = SceneBatch.offsets_for([5, 0, 7], [2, 3, 1], [4, 4, 2], [3, 3, 1, 1, 1, 2])
+    assert off["point"].tolist() == [0, 5, 5, 12]
+    assert off["view"].tolist() == [0, 2, 5, 6]
+    assert off["mask"].tolist() == [0, 10, 10, 17]
+    assert off["wobj"].tolist() == [0, 8, 20, 22]
+    assert off["feat"].tolist() == [0, 3, 6, 7, 8, 9, 11]
+    assert off["view_scene"].tolist() == [0, 0, 1, 1, 1, 2]
+
+
+def test_install_aliases_reference_module_names():
+    from dropclip_b200 import install
+    saved = {k: sys.modules.get(k) for k in install.ALIASES}
+    try:
+        install.install(voxelizer=True)
+        import importlib
+        ff = importlib.import_module("utils.feature_fusion")
+        ms = importlib.import_module("models.similarity")
+        pj = importlib.import_module("utils.projections")
+        assert ff.MultiviewFeatureFusion.__module__ == "dropclip_b200.feature_fusion"
+        assert ms.ClipSimilarity.NEGATIVE_PROMPT_GENERIC == ["object", "thing", "texture", "stuff"]
+        assert ms.ClipSimilarity.SOFTMAX_TEMP == 0.1
+        assert hasattr(pj, "depth_to_pointcloud") and hasattr(pj, "pool_multiview_features")
+        import MinkowskiEngine as ME
+        assert callable(ME.utils.sparse_quantize) and callable(ME.utils.sparse_collate)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        sys.modules.pop("MinkowskiEngine", None)
+        sys.modules.pop("MinkowskiEngine.utils", None)
+
+
+def test_reference_signatures_are_mirrored():
+    import inspect
+    from dropclip_b200.feature_fusion import MultiviewFeatureFusion as M
+    from dropclip_b200.similarity import ClipSimilarity as C
+    sig = inspect.signature(M.__init__)
+    assert list(sig.parameters)[1:] == ["camera_intrinsic", "visibility_threshold", "image_size", "patch_size",
+                                        "feature_size", "use_visibility", "use_similarity", "use_sim_kernel",
+                                        "use_obj_prior", "norm_feat", "device"]
+    assert sig.parameters["visibility_threshold"].default == 0.05 and sig.parameters["image_size"].default == (480, 640)
+    assert list(inspect.signature(M.fuse_obj_prior).parameters)[1:] == [
+        "points", "colors", "labels", "depths", "seg_masks", "camera_poses", "mv_features", "query_embeddings",
+        "return_obj", "device"]
+    assert list(inspect.signature(M.fuse_points).parameters)[1:] == [
+        "points", "colors", "labels", "depths", "seg_masks", "camera_poses", "mv_features", "query_embeddings", "device"]
+    assert list(inspect.signature(C.predict).parameters)[1:] == ["vis_feats", "qpos", "qneg", "norm_vis_feat", "method",
+                                                                 "threshold"]
+    assert list(inspect.signature(C.compute_similarity).parameters)[1:] == ["vis_feat_norm", "qpos", "qneg",
+                                                                            "softmax_temp", "method"]
+
+
+def test_shard_tables():
+    from dropclip_b200 import shard
+    assert shard.strided_shard(10, 1, 4) == [1, 5, 9]
+    parts = [shard.contiguous_shard(100, 110, r, 3) for r in range(3)]
+    assert sum(parts, []) == list(range(100, 111)) and [len(p) for p in parts] == [3, 3, 5]
+    bal = shard.balanced_shard([9, 1, 1, 1, 8, 2, 2, 2], 2)
+    assert sorted(sum(bal, [])) == list(range(8))
+    loads = [sum([9, 1, 1, 1, 8, 2, 2, 2][i] for i in b) for b in bal]
+    assert abs(loads[0] - loads[1]) <= 1
+
+
+def test_scene_writer_restart_semantics(tmp_path):
+    from dropclip_b200 import shard
+    per_obj = np.random.default_rng(0).standard_normal((4, 8)).astype(np.float32)
+    per_obj[0] = np.nan
+    q = np.ones((4, 8), np.float32)
+    p = shard.write_scene(str(tmp_path), 12, per_obj, q, np.zeros((5, 3)), np.zeros((5, 3)), np.arange(5), np.ones((2, 5)))
+    z = np.load(p)
+    assert np.array_equal(z["multiview/per_obj"][0], q[0]) and np.array_equal(z["multiview/per_obj"][1:], per_obj[1:])
+    assert z["pointcloud/label"].dtype == np.uint8 and z["pointcloud/vis_mask"].dtype == np.float32
+    assert shard.pending_scenes(str(tmp_path), [11, 12, 13]) == [11, 13]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from dropclip_b200 import shard
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        n_scenes = 7
+        mine = shard.strided_shard(n_scenes, rank, world)
+        feats = [torch.full((3 + (i % 3), 16), float(i)) for i in mine]  # ragged Q per scene
+        allf = shard.gather_object_features(mine, feats, q_max=5)
+        assert sorted(allf) == list(range(n_scenes))
+        for i, f in allf.items():
+            assert f.shape == (3 + (i % 3), 16) and bool((f == float(i)).all())
+        m = shard.reduce_metric_sums(torch.tensor([float(rank + 1), 2.0]))
+        assert torch.allclose(m, torch.tensor([(1 + 2) / 2.0, 2.0]))
+        assert shard.max_over_ranks(float(rank)) == float(world - 1)
+        q.put((rank, "ok"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_scene_parallel_gather_and_reduce_on_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=5)[0] for _ in range(2)) == [0, 1]
