@@ -49,6 +49,10 @@ SIGNATURES = {
     "dc_backproject": (c_int, [P, c_int, c_int, c_int, P, c_int, c_int, P, P, P]),
     "dc_points_to_pixels": (c_int, [P, c_int64, P, P, P]),
     "dc_transform_points": (c_int, [P, c_int64, P, P, P]),
+    "dc_sort_workspace": (c_size_t, [c_int64]),
+    "dc_unique_max_pool": (c_int, [P, P, c_int, c_int, c_int64, P, P, P, P, c_size_t, P]),
+    "dc_voxel_down_mean": (c_int, [P, c_int64, c_double, P, P, P, P, c_size_t, P]),
+    "dc_nearest_index": (c_int, [P, c_int64, P, c_int64, P, P, P]),
 }
 
 _lib = None

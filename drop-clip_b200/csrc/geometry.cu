@@ -22,10 +22,16 @@ __global__ void __launch_bounds__(256) backproject_kernel(const float* __restric
     const int y = (int)(pix / width), x = (int)(pix - (int64_t)y * width);
     const double z = (double)depths[t];
     // ((u - cx) / fx) * z : subtraction, division, multiplication are separate roundings in numpy
-    double px = __dmul_rn(__ddiv_rn(__dsub_rn((double)x, cx), fx), z);
-    double py = __dmul_rn(__ddiv_rn(__dsub_rn((double)y, cy), fy), z);
+    double px, py;
+    if (flip_y & 2) {  // Open3D create_from_rgbd_image: (u - cx) * z / fx
+      px = __ddiv_rn(__dmul_rn(__dsub_rn((double)x, cx), z), fx);
+      py = __ddiv_rn(__dmul_rn(__dsub_rn((double)y, cy), z), fy);
+    } else {           // utils/projections.py:75-81: ((u - cx) / fx) * z
+      px = __dmul_rn(__ddiv_rn(__dsub_rn((double)x, cx), fx), z);
+      py = __dmul_rn(__ddiv_rn(__dsub_rn((double)y, cy), fy), z);
+    }
     double pz = z;
-    if (flip_y) py = -py;
+    if (flip_y & 1) py = -py;
     if (flip_z) pz = -pz;
     if (poses) {
       const float* m = poses + (int64_t)v * 16;

@@ -249,8 +249,9 @@ DC_API int dc_minmax_threshold(float* values, int64_t n, const float* minmax, in
  * Geometry helpers of utils/projections.py.
  */
 /* depth_to_pointcloud utils/projections.py:67-86 (+ optional axis flips :89-97 and cam->world
- * utils/transforms.py:43-49): out[v, y, x, :] fp64. flip_y/flip_z negate after back-projection;
- * poses (fp32 [n_views,16], camera->world) may be NULL. */
+ * utils/transforms.py:43-49): out[v, y, x, :] fp64. flip_y bit0 / flip_z negate after back-projection;
+ * flip_y bit1 selects Open3D's rounding order (u - cx) * z / fx; poses (fp32 [n_views,16],
+ * camera->world) may be NULL. */
 DC_API int dc_backproject(const float* depths, int n_views, int height, int width, const double* fxfycxcy,
                    int flip_y, int flip_z, const float* poses, double* out, dc_stream_t stream);
 /* pointcloud_to_pixel utils/projections.py:59-64: un-truncated fp64 pixel coordinates. */
@@ -262,6 +263,28 @@ DC_API int dc_points_to_pixels(const double* cam_points, int64_t n, const double
  * _to_camera_frame utils/transforms.py:43-61 (the caller inverts the pose for the latter). */
 DC_API int dc_transform_points(const double* points, int64_t n, const float* matrix_host, double* out,
                         dc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sort-based helpers of the REGRAD-style functions in utils/projections.py.
+ * workspace for the three calls below: dc_sort_workspace(n) bytes.
+ */
+DC_API size_t dc_sort_workspace(int64_t n);
+/* pool_multiview_features utils/projections.py:245-261: np.unique(points, axis=0) (lexicographic
+ * order) + per-unique-row maximum of the features. points (n,3) fp64, feats (n,dim) DC_F32/DC_F64.
+ * Outputs hold n rows of capacity; *n_unique (device int64) gives the valid count. */
+DC_API int dc_unique_max_pool(const double* points, const void* feats, int feat_dtype, int dim, int64_t n,
+                       double* out_points, void* out_feats, int64_t* n_unique, void* workspace,
+                       size_t workspace_bytes, dc_stream_t stream);
+/* pc_voxel_down utils/geometry.py:350-352 (Open3D voxel_down_sample semantics, parity unpinned):
+ * voxel index = floor((p - (min_bound - size/2)) / size), output = mean of the voxel's points summed
+ * in point order; voxels ordered by index. first_index[u] = smallest point index of voxel u. */
+DC_API int dc_voxel_down_mean(const double* points, int64_t n, double voxel_size, double* out_points,
+                       int64_t* first_index, int64_t* n_voxels, void* workspace, size_t workspace_bytes,
+                       dc_stream_t stream);
+/* find_closest_indices utils/geometry.py:390-401 (cKDTree.query k=1): exact fp64 nearest neighbour
+ * of every query point in `ref` (ties: smallest index); out_dist2 (squared distance) may be NULL. */
+DC_API int dc_nearest_index(const double* query, int64_t m, const double* ref, int64_t n, int64_t* out_index,
+                     double* out_dist2, dc_stream_t stream);
 
 #ifdef __cplusplus
 }

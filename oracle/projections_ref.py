@@ -103,3 +103,81 @@ def sparse_collate_ref(coords_list, feats_list):
         c = np.asarray(c).astype(np.int32)
         out.append(np.concatenate([np.full((c.shape[0], 1), b, dtype=np.int32), c], axis=1))
     return np.concatenate(out, axis=0), np.concatenate([np.asarray(f) for f in feats_list], axis=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# REGRAD-style helpers (utils/projections.py:151-241, utils/geometry.py:350-352,390-401).
+# PARITY UNPINNED for voxel_down_ref: Open3D 0.15.2 is not installable here and the reference has
+# no fixture; the function restates Open3D's published voxel_down_sample semantics (voxel index =
+# floor((p - (min_bound - size/2)) / size), output = mean of the voxel's points summed in point
+# order). Output is ordered by voxel index (Open3D's own order is hash-map iteration order).
+def voxel_down_ref(points: np.ndarray, voxel_size: float):
+    pts = np.asarray(points, dtype=np.float64)
+    origin = pts.min(axis=0) - voxel_size * 0.5
+    idx = np.floor((pts - origin) / voxel_size).astype(np.int64)
+    key = (idx[:, 0] << 42) | (idx[:, 1] << 21) | idx[:, 2]
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    heads = np.r_[True, ks[1:] != ks[:-1]]
+    starts = np.flatnonzero(heads)
+    ends = np.r_[starts[1:], len(ks)]
+    out = np.empty((len(starts), 3))
+    first = np.empty(len(starts), dtype=np.int64)
+    for u, (a, b) in enumerate(zip(starts, ends)):
+        s = np.zeros(3)
+        for j in order[a:b]:  # sequential accumulation in point order, like Open3D's AccumulatedPoint
+            s = s + pts[j]
+        out[u] = s / float(b - a)
+        first[u] = order[a]
+    return out, first
+
+
+def nearest_ref(full_pc, filtered_pc):
+    import scipy.spatial
+    return scipy.spatial.cKDTree(full_pc).query(filtered_pc)[1]
+
+
+def camera_points_ref(pc, pose):
+    inv = np.linalg.inv(pose)
+    return np.dot(inv, np.vstack([pc.T, np.ones((1, pc.shape[0]))]))[:3, :].T
+
+
+def fuse_multiview_ref(pcs, feats, poses, intr, crop_size=336, patch_size=14, voxel_size=0.0075, reshape_feat=False,
+                       norm_feat=True):
+    """utils/projections.py:151-211 with pc_voxel_down -> voxel_down_ref."""
+    pc_aggr, _ = voxel_down_ref(np.concatenate(pcs, axis=0), voxel_size)
+    n, C = pc_aggr.shape[0], feats.shape[-1]
+    ph = pw = crop_size // patch_size
+    sums = torch.zeros((n, C), dtype=float)
+    counter = torch.zeros((n, 1), dtype=float)
+    for pc, feat, pose in zip(pcs, feats, poses):
+        ids, first = np.unique(nearest_ref(pc_aggr, pc), return_index=True)
+        cam = camera_points_ref(pc, pose)
+        cam[:, 2] = -cam[:, 2]
+        cam[:, 1] = -cam[:, 1]
+        mapping = pixels_of(cam, intr)
+        pixels = mapping[first].squeeze().astype(int)
+        if len(pixels.shape) < 2:
+            continue
+        ys = np.clip(pixels[:, 1], 0, intr["height"] - 1)
+        xs = np.clip(pixels[:, 0], 0, intr["width"] - 1)
+        if reshape_feat:
+            feat = feat.reshape(ph, pw, C)
+        if norm_feat:
+            feat /= feat.norm(dim=-1, keepdim=True)
+        full = nearest_patch_map(feat, (intr["height"], intr["width"], 3))
+        sums[ids, :] = sums[ids, :] + full[ys, xs]
+        counter[ids, :] += 1
+    counter[counter == 0] = 1e-5
+    return sums / counter, pc_aggr
+
+
+def rgbd_points_ref(rgb, depth, intr, depth_scale=1.0, depth_trunc=25.0):
+    """Open3D create_from_rgbd_image (convert_rgb_to_intensity=False) restated. PARITY UNPINNED."""
+    d = depth.astype(np.float32) / np.float32(depth_scale)
+    d = np.where(d >= depth_trunc, np.float32(0), d)
+    v, u = np.nonzero(d > 0)
+    z = d[v, u].astype(np.float64)
+    x = (u - intr["cx"]) * z / intr["fx"]
+    y = (v - intr["cy"]) * z / intr["fy"]
+    return np.stack([x, y, z], axis=1), rgb[v, u].astype(np.float64) / 255.0

@@ -419,3 +419,69 @@ def test_scatter_twin_feat_label():
     want = feat[label].clone()
     want[label == 0] = 0
     assert torch.equal(out, want)
+
+
+# ---------------------------------------------------------------------------------------------- REGRAD-style helpers
+def test_pool_multiview_features_vs_reference_golden():
+    from dropclip_b200 import projections as pj
+    z = gio.load("proj.npz")
+    u, f = pj.pool_multiview_features(z["pool_in_pts"], z["pool_in_feat"])
+    assert np.array_equal(u, z["pool_pts"]) and np.array_equal(f, z["pool_feat"])
+    rng = np.random.default_rng(4)  # larger, exercises the global bitonic stages; compare with numpy
+    pts = np.round(rng.uniform(-2, 2, size=(70_000, 3)) * 8) / 8
+    pts[::7] = -0.0
+    feat = rng.standard_normal((70_000, 5))
+    from oracle import projections_ref
+    ru, rf = projections_ref.unique_max_pool(pts, feat)
+    u, f = pj.pool_multiview_features(pts, feat)
+    assert np.array_equal(u, ru) and np.array_equal(f, rf) and f.dtype == np.float64
+
+
+def test_voxel_down_and_nearest_vs_restatements():
+    from dropclip_b200 import geometry as geo
+    from oracle import projections_ref
+    rng = np.random.default_rng(6)
+    pts = rng.uniform(-1, 1, size=(20_000, 3))
+    want, first = projections_ref.voxel_down_ref(pts, 0.05)
+    got, gfirst = geo.voxel_down(pts, 0.05, return_first_index=True)
+    assert np.array_equal(got.cpu().numpy(), want)  # same sums in the same order -> bit-exact
+    assert np.array_equal(gfirst.cpu().numpy(), first)
+    q = rng.uniform(-1, 1, size=(5000, 3))
+    assert np.array_equal(geo.find_closest_indices(want, q), projections_ref.nearest_ref(want, q))
+
+
+def test_regrad_fusion_and_rgbd_vs_restatements():
+    from dropclip_b200 import geometry as geo
+    from dropclip_b200 import projections as pj
+    from dropclip_b200.scenes import small_scene
+    from oracle import projections_ref
+    sc = small_scene(77, n_views=3, n_points=100, n_objects=4, height=84, width=84)
+    intr = dict(sc.intrinsic)
+    pcs, labels = [], []
+    for v in range(3):
+        cam = projections_ref.back_project(sc.depths[v], intr).reshape(-1, 3)[::5].copy()
+        cam[:, 2] = -cam[:, 2]
+        cam[:, 1] = -cam[:, 1]
+        pcs.append(projections_ref.to_world(cam, sc.camera_poses[v]))
+        labels.append(sc.seg_masks[v].reshape(-1)[::5])
+    g = torch.Generator().manual_seed(1)
+    feats = torch.randn((3, 6, 6, 32), generator=g)
+    want, want_pc = projections_ref.fuse_multiview_ref(pcs, feats.clone(), sc.camera_poses, intr, crop_size=84,
+                                                       patch_size=14, voxel_size=0.3)
+    got, got_pc = pj.fuse_multiview_features(pcs, feats.clone(), sc.camera_poses, intr, crop_size=84, patch_size=14,
+                                             voxel_size=0.3)
+    assert np.array_equal(got_pc, want_pc) and got.dtype == torch.float64
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-6, atol=1e-9)
+    # object-prior variant: label transfer + unweighted mean over views + broadcast (fp16)
+    obj_feats = [torch.randn((4, 32), generator=g).half() for _ in range(3)]
+    out, pc2, per_obj = pj.fuse_multiview_features_obj_prior(pcs, labels, obj_feats, [0, 1, 2, 3], voxel_size=0.3)
+    raw, raw_l = np.concatenate(pcs), np.concatenate(labels)
+    lab = raw_l[projections_ref.nearest_ref(raw, want_pc)]
+    ref_obj = torch.stack([torch.stack([f[i] for f in obj_feats]).mean(0) for i in range(4)])
+    assert out.dtype == torch.half and np.array_equal(pc2, want_pc)
+    assert torch.equal(out.cpu(), ref_obj[torch.from_numpy(lab)]) and torch.equal(per_obj, ref_obj)
+    # RGB-D back-projection with Open3D's conventions
+    rgb = np.random.default_rng(0).integers(0, 255, size=(84, 84, 3), dtype=np.uint8)
+    pcd = geo.rgbd_to_pointcloud_o3d(rgb, sc.depths[0], intr, depth_trunc=25.0)
+    rp, rc = projections_ref.rgbd_points_ref(rgb, sc.depths[0], intr, depth_trunc=25.0)
+    assert np.array_equal(pcd.points, rp) and np.array_equal(pcd.colors, rc)
