@@ -215,14 +215,14 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(const uint32_t* __res
 // Point-major: a thread owns one kept point and walks the views, so the flag and the rank are
 // read once per point instead of once per (view, point); reads and writes stay coalesced along
 // the point axis because ranks are monotone in the point index.
-template <typename T>
+template <typename T, typename TOut = T>
 __global__ void __launch_bounds__(256) compact_mask_kernel(const T* __restrict__ mask, const int64_t* __restrict__ mask_off,
                                                            const int64_t* __restrict__ point_off,
                                                            const int64_t* __restrict__ view_off,
                                                            const uint8_t* __restrict__ flags,
                                                            const int64_t* __restrict__ new_index,
                                                            const int64_t* __restrict__ kept_off,
-                                                           const int64_t* __restrict__ out_off, T* __restrict__ out) {
+                                                           const int64_t* __restrict__ out_off, TOut* __restrict__ out) {
   const int scene = blockIdx.y;
   const int64_t p0 = point_off[scene];
   const int64_t n = point_off[scene + 1] - p0;
@@ -232,9 +232,9 @@ __global__ void __launch_bounds__(256) compact_mask_kernel(const T* __restrict__
   const int64_t kept0 = kept_off[scene];
   const int64_t n_kept = kept_off[scene + 1] - kept0;
   const T* src = mask + mask_off[scene] + i;
-  T* dst = out + out_off[scene] + (new_index[p0 + i] - kept0);
+  TOut* dst = out + out_off[scene] + (new_index[p0 + i] - kept0);
 #pragma unroll 4
-  for (int v = 0; v < n_v; ++v) dst[(int64_t)v * n_kept] = src[(int64_t)v * n];
+  for (int v = 0; v < n_v; ++v) dst[(int64_t)v * n_kept] = (TOut)src[(int64_t)v * n];
 }
 
 }  // namespace
@@ -328,13 +328,16 @@ int dc_compact_mask(const void* mask, int elem_size, const int64_t* mask_off, co
                     dc_stream_t stream) {
   DC_CHECK_ARG(mask && mask_off && point_off && view_off && any_visible && new_index && kept_off && out_off && out,
                "dc_compact_mask: null pointer argument");
-  DC_CHECK_ARG(elem_size == 1 || elem_size == 4 || elem_size == 8, "dc_compact_mask: elem_size must be 1, 4 or 8");
+  DC_CHECK_ARG(elem_size == 1 || elem_size == 4 || elem_size == 8 || elem_size == 18,
+               "dc_compact_mask: elem_size must be 1, 4, 8 or 18 (uint8 in, int64 out)");
   if (n_scenes <= 0 || max_points_per_scene <= 0 || max_views_per_scene <= 0) return DC_OK;
   DC_CHECK_ARG(n_scenes <= 65535, "dc_compact_mask: at most 65535 scenes per call");
   (void)max_views_per_scene;
   dim3 grid((unsigned)dc::ceil_div<int64_t>(max_points_per_scene, 256), (unsigned)n_scenes);
   cudaStream_t st = dc::as_stream(stream);
-  if (elem_size == 1)
+  if (elem_size == 18)
+    compact_mask_kernel<uint8_t, long long><<<grid, 256, 0, st>>>((const uint8_t*)mask, mask_off, point_off, view_off, any_visible, new_index, kept_off, out_off, (long long*)out);
+  else if (elem_size == 1)
     compact_mask_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)mask, mask_off, point_off, view_off, any_visible, new_index, kept_off, out_off, (uint8_t*)out);
   else if (elem_size == 4)
     compact_mask_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)mask, mask_off, point_off, view_off, any_visible, new_index, kept_off, out_off, (uint32_t*)out);

@@ -230,9 +230,10 @@ class PinnedStaging:
         self._event = torch.cuda.Event()
         self._event.record()
 
-    def upload_list(self, arrays, dtype: torch.dtype, item_shape) -> torch.Tensor:
+    def upload_list(self, arrays, dtype: torch.dtype, item_shape, group_bytes: int = 24 << 20) -> torch.Tensor:
         """Stacks a list of equally-shaped host arrays straight into one pinned buffer (one host
-        copy per array instead of np.stack + a second copy) and uploads it."""
+        copy per array instead of np.stack + a second copy) and uploads it group by group, so the
+        H2D copy of group g overlaps the host copy of group g+1 (both run near DRAM / PCIe speed)."""
         n = len(arrays)
         numel = int(np.prod(item_shape)) if len(item_shape) else 1
         if self._slot == len(self._bufs):
@@ -243,11 +244,28 @@ class PinnedStaging:
             self._bufs[self._slot] = buf
         self._slot += 1
         view = buf[: n * numel].view((n,) + tuple(item_shape))
-        for i, a in enumerate(arrays):
-            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a))
-            view[i].copy_(t.reshape(item_shape))  # converts dtype if needed
+        out = torch.empty((n,) + tuple(item_shape), dtype=dtype, device=self.device)
+        per_group = max(1, group_bytes // max(1, numel * buf.element_size()))
+        for g0 in range(0, n, per_group):
+            g1 = min(n, g0 + per_group)
+            for i in range(g0, g1):
+                a = arrays[i]
+                t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a))
+                view[i].copy_(t.reshape(item_shape))  # converts dtype if needed
+            out[g0:g1].copy_(view[g0:g1], non_blocking=True)
         self.bytes_uploaded += n * numel * buf.element_size()
-        return view.to(self.device, non_blocking=True)
+        return out
+
+    def download(self, t: torch.Tensor) -> torch.Tensor:
+        """Async device->host copy into a reusable pinned buffer; valid until the next download()."""
+        n = t.numel()
+        buf = getattr(self, "_down", None)
+        if buf is None or buf.dtype != t.dtype or buf.numel() < n:
+            buf = torch.empty(max(n, 1), dtype=t.dtype, pin_memory=True)
+            self._down = buf
+        view = buf[:n].view(t.shape)
+        view.copy_(t, non_blocking=True)
+        return view
 
     def upload(self, arr) -> torch.Tensor:
         t = arr if isinstance(arr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(arr))
@@ -317,6 +335,63 @@ class FusionEngine:
         self.launches += 1
         return mask, any_vis, pobj
 
+    def visibility_sorted(self, b: SceneBatch, threshold: float = 0.05):
+        """Sorted-gather variant: returns (records [words, sum N] u32, rank [sum N] i64, any_visible)."""
+        n = b.total_points
+        words = (max(b.n_views, default=0) + 31) // 32
+        records = torch.empty((max(words, 1), max(n, 1)), dtype=torch.int32, device=b.device)
+        rank = torch.empty(max(n, 1), dtype=torch.int64, device=b.device)
+        any_vis = torch.empty(max(n, 1), dtype=torch.uint8, device=b.device)
+        ws_bytes = self.lib.dc_visibility_sorted_workspace(n, b.n_scenes)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=b.device)
+        with self._tick("project_visibility"):
+            check(self.lib.dc_project_visibility_sorted(
+                ptr(b.points), ptr(b.off["point"]), ptr(b.off["view"]), ptr(b.depths), ptr(b.inv_poses), ptr(b.intrinsics),
+                b.n_scenes, n, max(b.n_points, default=0), max(b.n_views, default=0), b.height, b.width, float(threshold),
+                ptr(records), ptr(rank), ptr(any_vis), ptr(ws), ws_bytes, current_stream()))
+        self.launches += 6
+        return records, rank, any_vis[:n]
+
+    def unpack_visibility(self, b: SceneBatch, records, rank, mask_dtype=torch.uint8):
+        mask = torch.empty(int(b.off_host["mask"][-1]), dtype=mask_dtype, device=b.device)
+        check(self.lib.dc_unpack_visibility(ptr(records), ptr(rank), ptr(b.off["point"]), ptr(b.off["view"]), ptr(b.off["mask"]),
+                                            b.n_scenes, b.total_points, max(b.n_points, default=0), ptr(mask),
+                                            mask.element_size(), current_stream()))
+        self.launches += 1
+        return mask
+
+    def compact_visibility(self, b: SceneBatch, any_vis, records, rank, out_dtype=torch.uint8,
+                           extra_rows: Sequence[torch.Tensor] = ()):
+        """Drops never-visible points and expands the bit records straight into the compacted masks.
+        Returns (new_index, kept_off, kept_host, out_off_host, compacted mask, compacted rows)."""
+        n = b.total_points
+        new_index = torch.empty(max(n, 1), dtype=torch.int64, device=b.device)
+        kept_off = torch.empty(b.n_scenes + 1, dtype=torch.int64, device=b.device)
+        ws_bytes = self.lib.dc_compact_workspace(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=b.device)
+        check(self.lib.dc_compact_scan(ptr(any_vis), n, ptr(b.off["point"]), b.n_scenes, ptr(new_index), ptr(kept_off),
+                                       ptr(ws), ws_bytes, current_stream()))
+        self.launches += 4
+        kept_host = kept_off.cpu().numpy()
+        out_off_host = _prefix([v * k for v, k in zip(b.n_views, np.diff(kept_host))])
+        out_off = torch.from_numpy(out_off_host).to(b.device)
+        cmask = torch.empty(int(out_off_host[-1]), dtype=out_dtype, device=b.device)
+        with self._tick("unpack_compact"):
+            check(self.lib.dc_unpack_visibility_compact(ptr(records), ptr(rank), ptr(b.off["point"]), ptr(b.off["view"]),
+                                                        ptr(any_vis), ptr(new_index), ptr(kept_off), ptr(out_off), b.n_scenes, n,
+                                                        max(b.n_points, default=0), ptr(cmask), cmask.element_size(),
+                                                        current_stream()))
+        self.launches += 1
+        rows_out = []
+        for t in extra_rows:
+            t2 = t.reshape(n, -1)
+            o = torch.empty((int(kept_host[-1]), t2.shape[1]), dtype=t.dtype, device=b.device)
+            check(self.lib.dc_compact_rows(ptr(t2), t2.shape[1] * t2.element_size(), ptr(any_vis), ptr(new_index), n,
+                                           ptr(o), current_stream()))
+            self.launches += 1
+            rows_out.append(o)
+        return new_index, kept_off, kept_host, out_off_host, cmask, rows_out
+
     def seg_tables(self, b: SceneBatch):
         """Instance histograms and the feature-row <-> object binding of every view."""
         tv = b.total_views
@@ -379,8 +454,10 @@ class FusionEngine:
         return out
 
     # ------------------------------------------------------------------ compaction
-    def compact(self, b: SceneBatch, any_vis, mask, extra_rows: Sequence[torch.Tensor] = ()):
-        """Drops never-visible points. Returns (new_index, kept_off (device), compacted mask, compacted rows)."""
+    def compact(self, b: SceneBatch, any_vis, mask, extra_rows: Sequence[torch.Tensor] = (), out_dtype=None):
+        """Drops never-visible points. Returns (new_index, kept_off (device), kept_off (host), mask offsets
+        (host), compacted mask, compacted rows). `out_dtype=torch.int64` widens a uint8 mask while
+        compacting (the reference's visibility mask is int64)."""
         n = b.total_points
         new_index = torch.empty(max(n, 1), dtype=torch.int64, device=b.device)
         kept_off = torch.empty(b.n_scenes + 1, dtype=torch.int64, device=b.device)
@@ -393,8 +470,11 @@ class FusionEngine:
         n_kept = np.diff(kept_host)
         out_off_host = _prefix([v * k for v, k in zip(b.n_views, n_kept)])
         out_off = torch.from_numpy(out_off_host).to(b.device)
-        cmask = torch.empty(int(out_off_host[-1]), dtype=mask.dtype, device=b.device)
-        check(self.lib.dc_compact_mask(ptr(mask), mask.element_size(), ptr(b.off["mask"]), ptr(b.off["point"]),
+        widen = out_dtype is not None and out_dtype != mask.dtype
+        if widen and not (mask.dtype == torch.uint8 and out_dtype == torch.int64):
+            raise ValueError("compact: only uint8 -> int64 widening is supported")
+        cmask = torch.empty(int(out_off_host[-1]), dtype=out_dtype if widen else mask.dtype, device=b.device)
+        check(self.lib.dc_compact_mask(ptr(mask), 18 if widen else mask.element_size(), ptr(b.off["mask"]), ptr(b.off["point"]),
                                        ptr(b.off["view"]), ptr(any_vis), ptr(new_index), ptr(kept_off), ptr(out_off),
                                        b.n_scenes, max(b.n_points, default=0), max(b.n_views, default=0), ptr(cmask),
                                        current_stream()))
@@ -411,13 +491,20 @@ class FusionEngine:
 
     # ------------------------------------------------------------------ whole object-level pass
     def fuse_object_level(self, b: SceneBatch, threshold=0.05, use_visibility=False, use_similarity=True,
-                          sim_kernel="max", mask_dtype=torch.uint8):
+                          sim_kernel="max", mask_dtype=torch.uint8, sorted_gather: bool = True):
         """Device-resident hot path of fuse_obj_prior (utils/feature_fusion.py:272-335) for a batch:
-        visibility -> instance tables -> view scores -> weights -> segmented weighted mean."""
-        mask, any_vis, _ = self.visibility(b, threshold, mask_dtype)
+        visibility -> instance tables -> view scores -> weights -> segmented weighted mean.
+        With `sorted_gather` the visibility result is returned as bit records (+ rank) to be expanded
+        by compact_visibility / unpack_visibility; otherwise as the full (V,N) mask blocks."""
+        out = {}
+        if sorted_gather:
+            out["records"], out["rank"], out["any_visible"] = self.visibility_sorted(b, threshold)
+        else:
+            out["mask"], out["any_visible"], _ = self.visibility(b, threshold, mask_dtype)
         tables = self.seg_tables(b)
         fused, weight = self.object_features(b, tables, use_visibility, use_similarity, sim_kernel)
-        return {"mask": mask, "any_visible": any_vis, "fused": fused, "weight_obj": weight, "view_status": tables[4]}
+        out.update({"fused": fused, "weight_obj": weight, "view_status": tables[4]})
+        return out
 
     # ------------------------------------------------------------------ pixel-level path
     def pixel_fuse(self, b: SceneBatch, mask_u8, sim_kernel, norm_feat: bool):

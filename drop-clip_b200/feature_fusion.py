@@ -108,8 +108,11 @@ class MultiviewFeatureFusion:
         if len(depths) == 0 or points.shape[0] == 0:
             return torch.zeros((len(depths), points.shape[0]), dtype=int)
         b = SceneBatch.from_host([self._scene(points, depths, camera_poses)], eng.device, staging=self._staging)
-        mask, _, _ = eng.visibility(b, self.visibility_threshold, torch.uint8)
-        return mask.view(len(depths), points.shape[0]).cpu().to(torch.int64)
+        records, rank, _ = eng.visibility_sorted(b, self.visibility_threshold)
+        mask = eng.unpack_visibility(b, records, rank, torch.int64)
+        staged = self._staging.download(mask.view(len(depths), points.shape[0]))
+        torch.cuda.current_stream().synchronize()
+        return staged.clone()
 
     # ------------------------------------------------------------------ a6
     @staticmethod
@@ -206,11 +209,16 @@ class MultiviewFeatureFusion:
             v = int(np.flatnonzero(status & 2)[0])
             raise IndexError(f"index {feats[v].shape[0]} is out of bounds for dimension 0 with size {feats[v].shape[0]}")
         extra = [b.labels.view(-1, 1)] if not return_obj else []
-        new_index, kept_off, kept_host, out_off_host, cmask, rows_out = eng.compact(b, res["any_visible"], res["mask"], extra)
+        new_index, kept_off, kept_host, out_off_host, cmask, rows_out = eng.compact_visibility(
+            b, res["any_visible"], res["records"], res["rank"], torch.int64, extra)
         n_kept = int(kept_host[-1])
+        # widened on the device, copied into fresh pinned memory (58 MB at V=73, N=100k: ~1 ms over PCIe
+        # instead of a ~4 ms uint8 -> int64 conversion on the host); overlaps the host-side row filtering
+        staged = self._staging.download(cmask.view(len(depths), n_kept))  # async D2H into reusable pinned memory
         keep = res["any_visible"].cpu().numpy().astype(bool)
         points, colors, labels = points[keep], colors[keep], labels[keep]
-        visibility_mask = cmask.view(len(depths), n_kept).cpu().to(torch.int64)
+        torch.cuda.current_stream().synchronize()
+        visibility_mask = staged.clone()  # ordinary CPU tensor, like the reference returns
         weight_obj = res["weight_obj"][: n_objects * n_views].view(n_objects, n_views)
         mv_feats_obj = res["fused"]
         if not return_obj:

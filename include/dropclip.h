@@ -87,6 +87,32 @@ DC_API int dc_project_visibility(const double* points, const int64_t* point_off,
                           void* mask, int mask_elem_size, uint8_t* any_visible,
                           const void* seg, int seg_dtype, int32_t* point_object, dc_stream_t stream);
 
+/* Same results as dc_project_visibility, organised for throughput on unordered clouds: points are
+ * counting-sorted by a coarse Morton cell per scene so that the depth gathers of a warp fall on a
+ * few cache lines, visibility is evaluated in sorted order and bit-packed:
+ *   records [ceil(max_views/32)][total_points] uint32, bit (v & 31) of word v/32 at the point's
+ *           sorted position;  rank [total_points] = sorted position of each point inside its scene.
+ * dc_unpack_visibility expands the records into the (V_s, N_s) mask blocks (mask_elem_size 1 or 8);
+ * dc_unpack_visibility_compact writes only the points with any_visible != 0 at their compacted
+ * rank (new_index / kept_off from dc_compact_scan, out_off = prefix of V_s * N'_s), i.e. the mask
+ * fuse_obj_prior returns (utils/feature_fusion.py:277-281) without materialising the full one.
+ * workspace: dc_visibility_sorted_workspace(total_points, n_scenes) bytes. */
+DC_API size_t dc_visibility_sorted_workspace(int64_t total_points, int n_scenes);
+DC_API int dc_project_visibility_sorted(const double* points, const int64_t* point_off, const int64_t* view_off,
+                                 const float* depths, const float* inv_poses, const double* intrinsics,
+                                 int n_scenes, int64_t total_points, int64_t max_points_per_scene,
+                                 int max_views_per_scene, int height, int width, double threshold,
+                                 uint32_t* records, int64_t* rank, uint8_t* any_visible, void* workspace,
+                                 size_t workspace_bytes, dc_stream_t stream);
+DC_API int dc_unpack_visibility(const uint32_t* records, const int64_t* rank, const int64_t* point_off,
+                         const int64_t* view_off, const int64_t* mask_off, int n_scenes, int64_t total_points,
+                         int64_t max_points_per_scene, void* mask, int mask_elem_size, dc_stream_t stream);
+DC_API int dc_unpack_visibility_compact(const uint32_t* records, const int64_t* rank, const int64_t* point_off,
+                                 const int64_t* view_off, const uint8_t* any_visible, const int64_t* new_index,
+                                 const int64_t* kept_off, const int64_t* out_off, int n_scenes,
+                                 int64_t total_points, int64_t max_points_per_scene, void* out,
+                                 int out_elem_size, dc_stream_t stream);
+
 /* Per-view instance histogram: counts[g*nbins + id] = #pixels of view g with that id,
  * outside[g] = #pixels whose id is not in [0,nbins). Replaces np.unique(seg)
  * utils/feature_fusion.py:307 and (seg == obj).sum() :320. seg_dtype: DC_U8 / DC_I32 / DC_I64. */
@@ -163,7 +189,8 @@ DC_API int dc_compact_scan(const uint8_t* any_visible, int64_t total_points, con
 DC_API int dc_compact_rows(const void* in, int64_t row_bytes, const uint8_t* any_visible, const int64_t* new_index,
                     int64_t total_points, void* out, dc_stream_t stream);
 /* Column compaction of the per-scene (V_s, N_s) masks into (V_s, N'_s) blocks at out_off[s]
- * (out_off = prefix of V_s * N'_s, computed by the caller from kept_off). elem_size 1, 4 or 8. */
+ * (out_off = prefix of V_s * N'_s, computed by the caller from kept_off). elem_size 1, 4 or 8;
+ * elem_size 18 reads a uint8 mask and writes int64 (the dtype the reference returns). */
 DC_API int dc_compact_mask(const void* mask, int elem_size, const int64_t* mask_off, const int64_t* point_off,
                     const int64_t* view_off, const uint8_t* any_visible, const int64_t* new_index,
                     const int64_t* kept_off, const int64_t* out_off, int n_scenes,

@@ -209,7 +209,8 @@ def test_object_level_batch_equals_single_scenes_and_oracle():
         (of, ow, ov), _ = fusion_ref.fuse_object_level(s.points, s.colors, s.labels, s.depths, s.seg_masks, s.camera_poses,
                                                        s.mv_features, s.query_embeddings, K, H, W, return_obj=True)
         full = fusion_ref.visibility_mask(s.points, s.depths, s.camera_poses, K, H, W).numpy()
-        got_mask = res["mask"][mo[i]:mo[i + 1]].view(s.n_views, s.n_points).cpu().numpy()
+        full_mask = eng.unpack_visibility(b, res["records"], res["rank"], torch.uint8)
+        got_mask = full_mask[mo[i]:mo[i + 1]].view(s.n_views, s.n_points).cpu().numpy()
         assert np.array_equal(got_mask.astype(np.int64), full)
         rel_close(res["fused"][qo[i]:qo[i + 1]].cpu().numpy(), of.numpy(), what=f"batch feat {i}")
         rel_close(res["weight_obj"][wo[i]:wo[i + 1]].view(-1, s.n_views).cpu().numpy(), ow.numpy(), what=f"batch w {i}")
@@ -485,3 +486,57 @@ def test_regrad_fusion_and_rgbd_vs_restatements():
     pcd = geo.rgbd_to_pointcloud_o3d(rgb, sc.depths[0], intr, depth_trunc=25.0)
     rp, rc = projections_ref.rgbd_points_ref(rgb, sc.depths[0], intr, depth_trunc=25.0)
     assert np.array_equal(pcd.points, rp) and np.array_equal(pcd.colors, rc)
+
+
+# ---------------------------------------------------------------------------------------------- sorted-gather visibility
+def test_sorted_visibility_equals_direct_kernel_and_golden():
+    """Counting-sorted + bit-packed pipeline == direct kernel == reference golden, on a ragged batch
+    that includes the adversarial points (non-finite, huge, on pixel borders)."""
+    from dropclip_b200.engine import FusionEngine, SceneBatch
+    eng = FusionEngine("cuda")
+    scenes, golds = [], []
+    for name in FUSE:
+        z = gio.load(name)
+        sc = gio.scene_of(z)
+        pts = np.concatenate([sc.points, z["adv_points"]])
+        scenes.append({"points": pts, "depths": sc.depths, "camera_poses": sc.camera_poses, "intrinsic": sc.intrinsic,
+                       "inv": sc.inv_poses})
+        golds.append(np.concatenate([gio.unpack(z["vis"], sc.n_points), gio.unpack(z["adv_vis"], z["adv_points"].shape[0])], axis=1))
+    for group in ([0], [1], [0, 1]):  # s0/s1 share the image size; s2 is larger
+        sub = [scenes[i] for i in group]
+        b = SceneBatch.from_host(sub, "cuda", inv_poses=[s["inv"] for s in sub])
+        direct, any_d, _ = eng.visibility(b, 0.05, torch.uint8)
+        records, rank, any_s = eng.visibility_sorted(b, 0.05)
+        for dt in (torch.uint8, torch.int64):
+            full = eng.unpack_visibility(b, records, rank, dt)
+            assert torch.equal(full.to(torch.uint8), direct)
+        assert torch.equal(any_s, any_d)
+        mo = b.off_host["mask"]
+        for k, i in enumerate(group):
+            got = direct[mo[k]:mo[k + 1]].view(len(sub[k]["depths"]), -1).cpu().numpy()
+            assert np.array_equal(got, golds[i])
+        # fused unpack + compaction == boolean column selection of the full mask
+        _, _, kept_host, out_off, cmask, rows = eng.compact_visibility(b, any_s, records, rank, torch.int64,
+                                                                       [b.points])
+        keep = any_d.cpu().numpy().astype(bool)
+        po = b.off_host["point"]
+        for k in range(len(sub)):
+            V = len(sub[k]["depths"])
+            want = direct[mo[k]:mo[k + 1]].view(V, -1).cpu().numpy()[:, keep[po[k]:po[k + 1]]]
+            got = cmask[out_off[k]:out_off[k + 1]].view(V, -1).cpu().numpy()
+            assert np.array_equal(got, want.astype(np.int64))
+        assert torch.equal(rows[0].cpu(), b.points.cpu()[torch.from_numpy(keep)])
+
+
+def test_sorted_visibility_full_size_scene_vs_direct():
+    """One MV-TOD-sized scene (73 views, 480x640, 100k points): both kernels must agree bit for bit."""
+    from dropclip_b200.engine import FusionEngine, batch_from_device
+    from dropclip_b200.scenes import make_scene
+    eng = FusionEngine("cuda")
+    sc = make_scene(4242, n_views=73, n_points=100_000, n_objects=21, device="cuda", as_torch=True)
+    b = batch_from_device([sc], "cuda")
+    direct, any_d, _ = eng.visibility(b, 0.05, torch.uint8)
+    records, rank, any_s = eng.visibility_sorted(b, 0.05)
+    assert torch.equal(eng.unpack_visibility(b, records, rank, torch.uint8), direct)
+    assert torch.equal(any_s, any_d)
+    assert 0.2 < direct.float().mean().item() < 0.9
