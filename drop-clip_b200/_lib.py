@@ -24,7 +24,8 @@ SIGNATURES = {
     "dc_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
     "dc_project_visibility": (c_int, [P, P, P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_double, P, c_int, P, P,
                                       c_int, P, P]),
-    "dc_visibility_sorted_workspace": (c_size_t, [c_int64, c_int]),
+    "dc_visibility_sorted_workspace": (c_size_t, [c_int64, c_int, c_int]),
+    "dc_visibility_sorted_groups": (c_int, [c_int, c_int64, c_int]),
     "dc_project_visibility_sorted": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int64, c_int, c_int, c_int, c_double, P, P, P,
                                              P, c_size_t, P]),
     "dc_unpack_visibility": (c_int, [P, P, P, P, P, c_int, c_int64, c_int64, P, c_int, P]),

@@ -9,8 +9,10 @@
 // Pipeline (all kernels scene-batched, results bit-identical to the direct kernel):
 //   1. bbox per scene (fp32 is enough: cells only steer locality, never results)
 //   2. counting sort by 15-bit Morton cell: histogram -> per-scene scan -> scatter (perm, rank)
-//   3. visibility in sorted order; results bit-packed per point (one 32-bit word per 32 views,
-//      plane-major so that lanes store contiguous words)
+//   3. visibility in sorted order - an fp32 filter with rigorous error bounds decides ~99.8 % of the
+//      (point, view) pairs, the rest is re-evaluated with the literal fp64 sequence from a per-warp
+//      queue (see "fp32 filter + exact fp64 queue" below); results bit-packed per point (one
+//      32-bit word per 32 views, plane-major so that lanes store contiguous words)
 //   4. unpack: a thread per original point reads its words through `rank` and writes the
 //      (V,N) mask rows coalesced - or, fused with the removal of never-visible points, writes the
 //      compacted (V,N') mask directly (the form fuse_obj_prior returns, utils/feature_fusion.py
@@ -22,26 +24,27 @@ namespace {
 using namespace dc::vis;
 
 constexpr int kThreads = 256;
-constexpr int kPointsPerThread = 2;
-constexpr int kPointsPerBlock = kThreads * kPointsPerThread;
 constexpr int kCellBits = 5;                    // per axis
 constexpr int kCells = 1 << (3 * kCellBits);    // 32768 bins per scene
+constexpr float kHuge = 1e15f;                  // coordinates beyond this never enter the fp32 filter
 
 struct SortedWs {
   float* bbox;        // [n_scenes][6] min xyz, max xyz
   int* counts;        // [n_scenes][kCells]
   int64_t* perm;      // [total_points] scene-local point index at each sorted position
+  void* view_consts;  // [n_scenes][max_views] ViewConst
   size_t total;
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-SortedWs carve(void* ws, int64_t total_points, int n_scenes) {
+SortedWs carve(void* ws, int64_t total_points, int n_scenes, int max_views) {
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
   const size_t o_bbox = take(sizeof(float) * 6 * (size_t)n_scenes);
   const size_t o_counts = take(sizeof(int) * (size_t)kCells * (size_t)n_scenes);
   const size_t o_perm = take(sizeof(int64_t) * (size_t)(total_points > 0 ? total_points : 1));
+  const size_t o_vc = take((size_t)80 * (size_t)n_scenes * (size_t)(max_views > 0 ? max_views : 1));
   SortedWs w{};
   w.total = off;
   if (ws) {
@@ -49,6 +52,7 @@ SortedWs carve(void* ws, int64_t total_points, int n_scenes) {
     w.bbox = reinterpret_cast<float*>(b + o_bbox);
     w.counts = reinterpret_cast<int*>(b + o_counts);
     w.perm = reinterpret_cast<int64_t*>(b + o_perm);
+    w.view_consts = b + o_vc;
   }
   return w;
 }
@@ -69,7 +73,7 @@ __global__ void init_bbox_kernel(float* bbox, int n_scenes) {
 
 __device__ __forceinline__ float finite_or(double v, float alt) {
   const float f = (float)v;
-  return (fabsf(f) < 1e30f) ? f : alt;  // NaN / inf / huge coordinates do not stretch the grid
+  return (fabsf(f) < kHuge) ? f : alt;  // NaN / inf / huge coordinates do not stretch the grid (exact path only)
 }
 
 __global__ void __launch_bounds__(kThreads) bbox_kernel(const double* __restrict__ points, const int64_t* __restrict__ point_off,
@@ -170,7 +174,119 @@ __global__ void __launch_bounds__(kThreads) cell_scatter_kernel(const double* __
   }
 }
 
-struct SortedParams {
+// ---------------------------------------------------------------------------------------------
+// fp32 filter + exact fp64 queue
+//
+// The reference's arithmetic is fp64 (oracle/visibility_ref.c) and the result must match it bit for
+// bit, but only two facts per (point, view) are observable: the integer pixel and the outcome of
+// |depth - z| <= threshold. Both are decided here from an fp32 evaluation with a rigorous error
+// bound; a pair whose fp32 interval straddles a decision boundary (pixel edge, image border,
+// threshold) is pushed to a per-warp queue and re-evaluated later with the literal fp64 sequence
+// (`literal_pixel`), with all 32 lanes busy. On MV-TOD-shaped scenes ~0.2 % of the pairs take the
+// exact path (benchmarks/fp32_filter_model.py), so the fp64 pipe (1/2 rate, ~35 instructions per
+// pair in the previous kernel) is off the critical path.
+//
+// Error model (eps = 2^-24, u = 2^-53; x~ denotes fp32 quantities):
+//   P = K * [R|t]' (3x4, evaluated once per view in fp64, rows 1,2 of the inverse pose negated),
+//   q~_r = fp32 dot(P~_r, [p~;1]).  Rounding P and p to fp32 costs 2 eps per product, the chain at
+//   most 5 more roundings, the reference's own fp64 roundings ~10 u:  |q~_r - q_r| <= E_r :=
+//   8 eps * (sum_j |P_rj| * B_j + |P_r3|), B = per-scene bound on |coordinate| (from the bbox pass).
+//   r~ = rcp.approx(q~_z) (1 ulp) = (1 + eta) / q_z with |eta| <= rho := 1.03 E_z |r~| + 5 eps,
+//   valid while |q~_z| >= 1024 E_z.   u~ = q~_x * r~  =>
+//   |u~ - u| <= e_u := 1.02 (|u~| rho + E_x |r~|)            (same for v with E_y).
+//   The pair's pixel is decided when the fractional part of u~ and of v~ is farther than e from 0
+//   and 1 (so no integer lies between u~ and the reference's correctly rounded quotient); then
+//   floor(u_ref) = floor(u~), the reference's "trunc toward zero into [0, W)" test is
+//   -1 <= floor <= W-1 and its pixel is max(floor, 0)  (quirk q1: u in (-1, 0) lands on column 0).
+//   The depth test is decided when | |d - q~_z| - threshold | > E_z (+ fp32 rounding slack).
+// Anything non-finite, huge or degenerate fails a comparison and ends up in the exact queue.
+struct ViewConst {       // 20 floats = 80 B; 819 views fit the 64 KB constant bank
+  float P[12];           // fp32 image of K * inverse pose (rows 1,2 negated)
+  float ax, ay;          // 1.02 * E_x, 1.02 * E_y
+  float ez_rho;          // 1.02 * 1.03 * E_z
+  float zmin;            // 1024 * E_z; +inf disables the filter for this view (non-pinhole K, overflow)
+  float thr_lo, thr_hi;  // threshold -/+ E_z with directed rounding
+  float pad0, pad1;
+};
+static_assert(sizeof(ViewConst) == 80, "ViewConst layout");
+constexpr int kConstViews = 65536 / (int)sizeof(ViewConst);  // 819
+__constant__ ViewConst c_views[kConstViews];
+
+constexpr int kPts = 4;                        // points per thread
+constexpr int kTile = kThreads * kPts;         // points per CTA
+constexpr int kQueue = 256;                    // exact-path queue entries per warp
+constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23: x + kMagic (round down) = floor(x) + kMagic for |x| < 2^22
+
+// one thread per (scene, view slot): fp64 set-up of the filter constants
+__global__ void camera_prep_kernel(const float* __restrict__ inv_poses, const double* __restrict__ intrinsics,
+                                   const int64_t* __restrict__ view_off, const float* __restrict__ bbox, int n_scenes,
+                                   int max_views, double threshold, ViewConst* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_scenes * max_views) return;
+  const int scene = i / max_views, v = i - scene * max_views;
+  ViewConst c;
+#pragma unroll
+  for (int j = 0; j < 12; ++j) c.P[j] = 0.f;
+  c.ax = c.ay = c.ez_rho = 0.f;
+  c.zmin = INFINITY;
+  c.thr_lo = -INFINITY;
+  c.thr_hi = INFINITY;
+  c.pad0 = c.pad1 = 0.f;
+  const int64_t v0 = view_off[scene];
+  const int n_views = (int)(view_off[scene + 1] - v0);
+  if (v < n_views) {
+    double m[12];
+    bool ok = true;
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+      const double val = (double)__ldg(inv_poses + (v0 + v) * 16 + e);
+      ok &= fabs(val) < 1e30;
+      m[e] = (e >= 4) ? -val : val;
+    }
+    double K[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      K[e] = __ldg(intrinsics + (int64_t)scene * 9 + e);
+      ok &= fabs(K[e]) < 1e30;
+    }
+    ok &= (K[1] == 0.0 && K[3] == 0.0 && K[6] == 0.0 && K[7] == 0.0 && K[8] == 1.0);
+    const float* bb = bbox + scene * 6;
+    double B[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double lo = bb[a], hi = bb[3 + a];
+      B[a] = (lo <= hi) ? fmax(fabs(lo), fabs(hi)) * (1.0 + 1e-6) : 0.0;  // bbox holds fp32-rounded coordinates
+    }
+    double P[12], E[3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      P[j] = K[0] * m[j] + K[2] * m[8 + j];
+      P[4 + j] = K[4] * m[4 + j] + K[5] * m[8 + j];
+      P[8 + j] = m[8 + j];
+    }
+    const double eps = 5.9604644775390625e-08;  // 2^-24
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double S = fabs(P[4 * r]) * B[0] + fabs(P[4 * r + 1]) * B[1] + fabs(P[4 * r + 2]) * B[2] + fabs(P[4 * r + 3]);
+      ok &= S < 1e30;
+      E[r] = fmax(8.0 * eps * S * (1.0 + 1e-6), 1e-30);
+    }
+    if (ok) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) c.P[j] = (float)P[j];
+      c.ax = __double2float_ru(1.02 * E[0]);
+      c.ay = __double2float_ru(1.02 * E[1]);
+      c.ez_rho = __double2float_ru(1.02 * 1.03 * E[2]);
+      c.zmin = __double2float_ru(1024.0 * E[2]);
+      const double lo = threshold - E[2], hi = threshold + E[2];
+      c.thr_lo = __double2float_rd(lo - 4.0 * eps * fabs(lo) - 1e-30);   // NaN threshold: every comparison fails
+      c.thr_hi = __double2float_ru(hi + 4.0 * eps * fabs(hi) + 1e-30);
+    }
+  }
+  out[i] = c;
+}
+
+struct FastParams {
   const double* points;
   const int64_t* point_off;
   const int64_t* view_off;
@@ -179,74 +295,215 @@ struct SortedParams {
   const double* intrinsics;
   const int64_t* perm;
   int64_t total_points;
+  int scene0, max_views;
   int height, width;
+  float wf, cu, hu, cv, hv;  // width; centre and half-width of the admissible floor range [-1, limit - 1] per axis
+  float wm1, hm1;            // width - 1, height - 1
   double threshold;
   uint32_t* records;  // [n_words][total_points], indexed by sorted position
   uint8_t* any_visible;
 };
 
-__global__ void __launch_bounds__(kThreads, 4) visibility_sorted_kernel(SortedParams p) {
-  extern __shared__ double s_cam[];
-  __shared__ int s_ok;
-  const int scene = blockIdx.y;
+// Exact re-evaluation of the queued pairs of one warp (all lanes busy). Results are OR-ed into the
+// warp's slice of s_rec. Kept out of line so that its fp64 registers do not weigh on the filter loop.
+// `pts` / `perm` point at the scene's first point, `poses` / `depths` at its first view, `K` at its intrinsics.
+static __device__ __noinline__ void drain_queue(const uint32_t* __restrict__ queue, int count, int n_tile, const double* __restrict__ pts,
+                                                const int64_t* __restrict__ perm_tile, const float* __restrict__ poses,
+                                                const double* __restrict__ Kp, const float* __restrict__ depths, int width,
+                                                int height, double threshold, uint32_t* __restrict__ s_rec) {
+  const int lane = threadIdx.x & 31;
+  double K[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) K[e] = __ldg(Kp + e);
+  const int64_t hw = (int64_t)height * width;
+  for (int i = lane; i < count; i += 32) {
+    const uint32_t entry = queue[i];
+    const int v = (int)(entry >> 12), local = (int)(entry & 4095u);
+    const int64_t orig = __ldg(perm_tile + (local < n_tile ? local : n_tile - 1));  // padding slots repeat the last point
+    const double x = __ldg(pts + 3 * orig), y = __ldg(pts + 3 * orig + 1), z = __ldg(pts + 3 * orig + 2);
+    double m[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+      const double val = (double)__ldg(poses + (int64_t)v * 16 + e);
+      m[e] = (e >= 4) ? -val : val;
+    }
+    int pix;
+    double qz;
+    bool vis = literal_pixel(m, K, x, y, z, width, height, pix, qz);
+    if (vis) vis = fabs((double)__ldg(depths + (int64_t)v * hw + pix) - qz) <= threshold;
+    if (vis) atomicOr(s_rec + (v >> 5) * kTile + local, 1u << (v & 31));
+  }
+}
+
+// Stage A of one view for the kPts points of a thread: fp32 projection, pixel decision, and the depth
+// gather ISSUED as a 4-byte cp.async into the thread's own shared-memory slot. The loop below tests it
+// three stages later behind cp.async.wait_group, so the L2/DRAM latency of the gather is covered by
+// the arithmetic of the next views instead of by occupancy. (Plain loads cannot do this: ptxas puts
+// every LDG of the loop on one scoreboard, so a consumer of the oldest gather also waits for the
+// newest - measured as 18-28 % of all stall samples on that one instruction.)
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(__cvta_generic_to_global(gmem_src))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void stage_project(const ViewConst& c, const FastParams& p, const float* __restrict__ depth,
+                                              const float (&x)[kPts], const float (&y)[kPts], const float (&z)[kPts],
+                                              float (&qz_out)[kPts], float* __restrict__ s_slot) {
+  asm volatile("" : "+l"(depth));  // keep the view's base pointer in a register pair (one IMAD.WIDE per gather)
+#pragma unroll
+  for (int k = 0; k < kPts; ++k) {
+    const float qx = fmaf(c.P[0], x[k], fmaf(c.P[1], y[k], fmaf(c.P[2], z[k], c.P[3])));
+    const float qy = fmaf(c.P[4], x[k], fmaf(c.P[5], y[k], fmaf(c.P[6], z[k], c.P[7])));
+    const float qz = fmaf(c.P[8], x[k], fmaf(c.P[9], y[k], fmaf(c.P[10], z[k], c.P[11])));
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(qz));
+    const float ar = fabsf(r);
+    const float u = qx * r, w = qy * r;
+    const float rho = fmaf(c.ez_rho, ar, 3.04e-07f);                     // 1.02 * (1.03 E_z |r| + 5 eps)
+    const float h_u = fmaf(-fabsf(u), rho, fmaf(-c.ax, ar, 0.499999f));  // 0.5 - e_u - slack for the fp32 evaluation of e_u
+    const float h_v = fmaf(-fabsf(w), rho, fmaf(-c.ay, ar, 0.499999f));
+    const float fu = __fadd_rd(u, kMagic) - kMagic;  // floor(u) while |u| < 2^22 (guaranteed when h_u > 0)
+    const float fv = __fadd_rd(w, kMagic) - kMagic;
+    const float gu = (u - fu) - 0.5f, gv = (w - fv) - 0.5f;
+    const bool decided = (fabsf(qz) >= c.zmin) && (fabsf(gu) < h_u) && (fabsf(gv) < h_v);
+    const bool inside = (fabsf(fu - p.cu) <= p.hu) && (fabsf(fv - p.cv) <= p.hv);  // -1 <= floor <= limit - 1
+    // The gather is issued unconditionally at the pixel clamped into the image (no predicate has to
+    // outlive the arithmetic; NaN clamps to 0). integer-valued float < 2^23 -> index without a
+    // conversion instruction: the low mantissa bits of pix + 2^23 are the index.
+    const float fuc = fminf(fmaxf(fu, 0.f), p.wm1), fvc = fminf(fmaxf(fv, 0.f), p.hm1);
+    const unsigned pix = (unsigned)__float_as_int(fmaf(fvc, p.wf, fuc) + 8388608.0f) & 0x7fffffu;
+    cp_async_f32(s_slot + k * kThreads, depth + pix);
+    // No flag travels with the gather either. A pixel decided to be outside the image records
+    // z = +inf: |depth - inf| fails "<= thr_lo" and passes "> thr_hi" (decided, not visible). An
+    // undecided pixel records z = NaN, which fails both tests (-> exact queue), exactly like a NaN
+    // depth pixel would.
+    qz_out[k] = decided ? (inside ? qz : INFINITY) : __int_as_float(0x7fc00000);
+  }
+  cp_async_commit();
+}
+
+__global__ void __launch_bounds__(kThreads, 2) visibility_filter_kernel(const __grid_constant__ FastParams p) {
+  extern __shared__ uint32_t s_dyn[];  // [n_words][kTile] records, [8][kQueue] queues, [3][kTile] gathered depths
+  const int scene = p.scene0 + blockIdx.y;
   const int64_t p0 = p.point_off[scene];
   const int64_t n_pts = p.point_off[scene + 1] - p0;
-  const int64_t tile0 = (int64_t)blockIdx.x * kPointsPerBlock;
+  const int64_t tile0 = (int64_t)blockIdx.x * kTile;
   if (tile0 >= n_pts) return;
+  const int n_tile = (int)((n_pts - tile0 < kTile) ? (n_pts - tile0) : kTile);  // valid points of this tile
   const int64_t v0 = p.view_off[scene];
   const int n_views = (int)(p.view_off[scene + 1] - v0);
-  const bool pinhole = load_cameras(s_cam, &s_ok, p.inv_poses, v0, n_views, p.intrinsics, scene);
-  const double* s_K = s_cam + n_views * 12;
-  const double K0 = s_K[0], K2 = s_K[2], K4 = s_K[4], K5 = s_K[5];
+  const int n_words = (n_views + 31) >> 5;
+  uint32_t* s_rec = s_dyn;
+  uint32_t* s_queue = s_dyn + (size_t)((p.max_views + 31) >> 5) * kTile + (threadIdx.x >> 5) * kQueue;
+  float* s_sensor = reinterpret_cast<float*>(s_dyn + (size_t)((p.max_views + 31) >> 5) * kTile + (kThreads / 32) * kQueue) + threadIdx.x;
+  const int lane = threadIdx.x & 31;
 
-  double px[kPointsPerThread], py[kPointsPerThread], pz[kPointsPerThread];
-  bool valid[kPointsPerThread], fast[kPointsPerThread];
-  int64_t orig[kPointsPerThread];
-  uint32_t word[kPointsPerThread], any[kPointsPerThread];
+  // Slots past the end of the scene re-evaluate its last point (results are never written out), so
+  // the loop carries no per-point validity test. Points that must not enter the filter (non-finite
+  // or huge coordinates) carry NaN, which fails every comparison and lands in the exact queue.
+  float x[kPts], y[kPts], z[kPts];
+  uint32_t word[kPts];
 #pragma unroll
-  for (int k = 0; k < kPointsPerThread; ++k) {
-    const int64_t s = tile0 + k * kThreads + threadIdx.x;
-    valid[k] = s < n_pts;
-    orig[k] = valid[k] ? p0 + p.perm[p0 + s] : p0;
-    px[k] = __ldg(p.points + 3 * orig[k]);
-    py[k] = __ldg(p.points + 3 * orig[k] + 1);
-    pz[k] = __ldg(p.points + 3 * orig[k] + 2);
-    fast[k] = pinhole && fabs(px[k]) < kBig && fabs(py[k]) < kBig && fabs(pz[k]) < kBig;
+  for (int k = 0; k < kPts; ++k) {
+    const int local = k * kThreads + threadIdx.x;
+    const int64_t orig = p0 + __ldg(p.perm + p0 + tile0 + (local < n_tile ? local : n_tile - 1));
+    const float fx = (float)__ldg(p.points + 3 * orig), fy = (float)__ldg(p.points + 3 * orig + 1),
+                fz = (float)__ldg(p.points + 3 * orig + 2);
+    const bool tame = fabsf(fx) < kHuge && fabsf(fy) < kHuge && fabsf(fz) < kHuge;  // NaN -> false; same rule as the bbox pass
+    x[k] = tame ? fx : __int_as_float(0x7fc00000);
+    y[k] = fy;
+    z[k] = fz;
     word[k] = 0;
-    any[k] = 0;
+    for (int w = 0; w < n_words; ++w) s_rec[w * kTile + local] = 0;
+    for (int g = 0; g < 3; ++g) s_sensor[g * kTile + k * kThreads] = 0.f;  // slots never hold junk NaN/inf patterns
   }
+  __syncwarp();
   const int64_t hw = (int64_t)p.height * p.width;
-  for (int v = 0; v < n_views; ++v) {
-    const double* m = s_cam + v * 12;
-    const float* depth = p.depths + (v0 + v) * hw;
-    bool inside[kPointsPerThread];
-    int pix[kPointsPerThread];
-    double qz[kPointsPerThread];
+  const ViewConst* cviews = c_views + blockIdx.y * p.max_views;
+  const float* depth = p.depths + v0 * hw;
+  int qcount = 0;
+
+  // stage B of view v: depth test on the gathers issued three stages earlier, queue pushes, record flush
+  auto stage_test = [&](int v, const float (&qz)[kPts], const float* __restrict__ s_slot) {
+    const uint32_t bit = 1u << (v & 31);
+    const float thr_lo = cviews[v].thr_lo, thr_hi = cviews[v].thr_hi;
+    cp_async_wait<2>();  // all but the two most recent groups have landed
+    bool und[kPts], any_und = false;
 #pragma unroll
-    for (int k = 0; k < kPointsPerThread; ++k)
-      inside[k] = project_point(m, s_K, K0, K2, K4, K5, fast[k], px[k], py[k], pz[k], p.width, p.height, pix[k], qz[k]) && valid[k];
-    float sensor[kPointsPerThread];
+    for (int k = 0; k < kPts; ++k) {
+      const float delta = fabsf(s_slot[k * kThreads] - qz[k]);
+      const bool yes = delta <= thr_lo;
+      if (yes) word[k] |= bit;
+      und[k] = !yes && !(delta > thr_hi);
+      any_und |= und[k];
+    }
+    if (__any_sync(0xffffffffu, any_und)) {
 #pragma unroll
-    for (int k = 0; k < kPointsPerThread; ++k) sensor[k] = inside[k] ? __ldg(depth + pix[k]) : 0.f;
-#pragma unroll
-    for (int k = 0; k < kPointsPerThread; ++k) {
-      const bool vis = inside[k] && (fabs((double)sensor[k] - qz[k]) <= p.threshold);
-      word[k] |= (vis ? 1u : 0u) << (v & 31);
+      for (int k = 0; k < kPts; ++k) {
+        const bool mine = und[k];
+        const unsigned b = __ballot_sync(0xffffffffu, mine);
+        if (mine) s_queue[qcount + __popc(b & ((1u << lane) - 1u))] = ((uint32_t)v << 12) | (uint32_t)(k * kThreads + threadIdx.x);
+        qcount += __popc(b);
+      }
+      if (qcount > kQueue - 32 * kPts) {
+        __syncwarp();
+        drain_queue(s_queue, qcount, n_tile, p.points + 3 * p0, p.perm + p0 + tile0, p.inv_poses + v0 * 16,
+                    p.intrinsics + (int64_t)scene * 9, p.depths + v0 * hw, p.width, p.height, p.threshold, s_rec);
+        __syncwarp();
+        qcount = 0;
+      }
     }
     if ((v & 31) == 31 || v == n_views - 1) {
-      const int64_t plane = (int64_t)(v >> 5) * p.total_points + p0 + tile0 + threadIdx.x;
 #pragma unroll
-      for (int k = 0; k < kPointsPerThread; ++k) {
-        if (valid[k]) p.records[plane + k * kThreads] = word[k];
-        any[k] |= word[k];
+      for (int k = 0; k < kPts; ++k) {
+        s_rec[(v >> 5) * kTile + k * kThreads + threadIdx.x] |= word[k];  // warp-private slots: no race with drain's atomicOr
         word[k] = 0;
       }
     }
+  };
+
+  // Three gather groups rotate (the loop is unrolled by three): the gathers of view v + 3 are issued
+  // right after view v has been tested, two views of arithmetic before they are needed - enough to
+  // cover a DRAM miss. Every stage commits exactly one (possibly empty) group, so "all but the two
+  // most recent groups" always names the view under test.
+  float qa[kPts], qb[kPts], qc[kPts];
+  float* const sa = s_sensor;
+  float* const sb = s_sensor + kTile;
+  float* const sc = s_sensor + 2 * kTile;
+  if (n_views > 0) stage_project(cviews[0], p, depth, x, y, z, qa, sa); else cp_async_commit();
+  if (n_views > 1) stage_project(cviews[1], p, depth + hw, x, y, z, qb, sb); else cp_async_commit();
+  if (n_views > 2) stage_project(cviews[2], p, depth + 2 * hw, x, y, z, qc, sc); else cp_async_commit();
+  depth += 3 * hw;
+  for (int v = 0; v < n_views; v += 3, depth += 3 * hw) {
+    stage_test(v, qa, sa);
+    if (v + 3 < n_views) stage_project(cviews[v + 3], p, depth, x, y, z, qa, sa); else cp_async_commit();
+    if (v + 1 < n_views) stage_test(v + 1, qb, sb);
+    if (v + 4 < n_views) stage_project(cviews[v + 4], p, depth + hw, x, y, z, qb, sb); else cp_async_commit();
+    if (v + 2 < n_views) stage_test(v + 2, qc, sc);
+    if (v + 5 < n_views) stage_project(cviews[v + 5], p, depth + 2 * hw, x, y, z, qc, sc); else cp_async_commit();
   }
-  if (p.any_visible) {
+  cp_async_wait<0>();
+  __syncwarp();
+  if (qcount > 0)
+    drain_queue(s_queue, qcount, n_tile, p.points + 3 * p0, p.perm + p0 + tile0, p.inv_poses + v0 * 16,
+                p.intrinsics + (int64_t)scene * 9, p.depths + v0 * hw, p.width, p.height, p.threshold, s_rec);
+  __syncwarp();
 #pragma unroll
-    for (int k = 0; k < kPointsPerThread; ++k)
-      if (valid[k]) p.any_visible[orig[k]] = any[k] ? 1 : 0;
+  for (int k = 0; k < kPts; ++k) {
+    const int local = k * kThreads + threadIdx.x;
+    if (local >= n_tile) continue;
+    const int64_t s = tile0 + local;
+    uint32_t any = 0;
+    for (int w = 0; w < n_words; ++w) {
+      const uint32_t bits = s_rec[w * kTile + local];
+      p.records[(int64_t)w * p.total_points + p0 + s] = bits;
+      any |= bits;
+    }
+    if (p.any_visible) p.any_visible[p0 + __ldg(p.perm + p0 + s)] = any ? 1 : 0;
   }
 }
 
@@ -281,12 +538,30 @@ __global__ void __launch_bounds__(kThreads) unpack_kernel(const uint32_t* __rest
   }
 }
 
+
+
+// scenes per filter launch: bounded by the constant bank and by one full wave of CTAs; balanced
+int64_t scenes_per_group(int n_scenes, int64_t max_points_per_scene, int max_views_per_scene) {
+  const int64_t ctas_per_scene = dc::ceil_div<int64_t>(max_points_per_scene, kTile);
+  int64_t group = kConstViews / (max_views_per_scene > 0 ? max_views_per_scene : 1);
+  const int64_t wave = ((int64_t)dc::sm_count() * 8) / (ctas_per_scene > 0 ? ctas_per_scene : 1);  // a few CTAs per slot
+  if (wave >= 1 && group > wave) group = wave;
+  if (group < 1) group = 1;
+  const int64_t n_groups = dc::ceil_div<int64_t>(n_scenes, group);
+  return dc::ceil_div<int64_t>(n_scenes, n_groups);
+}
+
 }  // namespace
 
 extern "C" {
 
-size_t dc_visibility_sorted_workspace(int64_t total_points, int n_scenes) {
-  return carve(nullptr, total_points, n_scenes > 0 ? n_scenes : 1).total;
+int dc_visibility_sorted_groups(int n_scenes, int64_t max_points_per_scene, int max_views_per_scene) {
+  if (n_scenes <= 0 || max_points_per_scene <= 0 || max_views_per_scene <= 0) return 0;
+  return (int)dc::ceil_div<int64_t>(n_scenes, scenes_per_group(n_scenes, max_points_per_scene, max_views_per_scene));
+}
+
+size_t dc_visibility_sorted_workspace(int64_t total_points, int n_scenes, int max_views_per_scene) {
+  return carve(nullptr, total_points, n_scenes > 0 ? n_scenes : 1, max_views_per_scene).total;
 }
 
 int dc_project_visibility_sorted(const double* points, const int64_t* point_off, const int64_t* view_off, const float* depths,
@@ -300,9 +575,13 @@ int dc_project_visibility_sorted(const double* points, const int64_t* point_off,
   if (n_scenes <= 0 || max_points_per_scene <= 0 || total_points <= 0) return DC_OK;
   DC_CHECK_ARG(n_scenes <= 65535, "dc_project_visibility_sorted: at most 65535 scenes per call");
   DC_CHECK_ARG(max_points_per_scene < (1ll << 31), "dc_project_visibility_sorted: at most 2^31 points per scene");
-  const size_t smem = ((size_t)max_views_per_scene * 12 + 9) * sizeof(double);
-  DC_CHECK_ARG(smem <= 48 * 1024, "dc_project_visibility_sorted: too many views per scene (%d)", max_views_per_scene);
-  SortedWs w = carve(workspace, total_points, n_scenes);
+  DC_CHECK_ARG(max_views_per_scene > 0 && max_views_per_scene <= kConstViews && max_views_per_scene < (1 << 20),
+               "dc_project_visibility_sorted: 1..%d views per scene (%d)", kConstViews, max_views_per_scene);
+  DC_CHECK_ARG((int64_t)height * width <= (1 << 23), "dc_project_visibility_sorted: image too large for the fp32 pixel index");
+  const int n_words = (max_views_per_scene + 31) / 32;
+  const size_t smem = sizeof(uint32_t) * ((size_t)n_words * kTile + (size_t)(kThreads / 32) * kQueue + 3 * (size_t)kTile);
+  DC_CHECK_ARG(smem <= 200 * 1024, "dc_project_visibility_sorted: too many views per scene (%d)", max_views_per_scene);
+  SortedWs w = carve(workspace, total_points, n_scenes, max_views_per_scene);
   if (workspace_bytes < w.total)
     return dc::fail(DC_ERR_WORKSPACE, "dc_project_visibility_sorted: workspace %zu < %zu", workspace_bytes, w.total);
   cudaStream_t st = dc::as_stream(stream);
@@ -317,10 +596,28 @@ int dc_project_visibility_sorted(const double* points, const int64_t* point_off,
   cell_count_kernel<<<g1, kThreads, 0, st>>>(points, point_off, w.bbox, w.counts);
   cell_scan_kernel<<<(unsigned)n_scenes, 1024, 0, st>>>(w.counts);
   cell_scatter_kernel<<<g1, kThreads, 0, st>>>(points, point_off, w.bbox, w.counts, w.perm, rank);
-  SortedParams p{points, point_off, view_off, depths, inv_poses, intrinsics, w.perm, total_points, height, width, threshold,
-                 records, any_visible};
-  dim3 grid((unsigned)dc::ceil_div<int64_t>(max_points_per_scene, kPointsPerBlock), (unsigned)n_scenes);
-  visibility_sorted_kernel<<<grid, kThreads, smem, st>>>(p);
+  ViewConst* vc = reinterpret_cast<ViewConst*>(w.view_consts);
+  camera_prep_kernel<<<dc::ceil_div(n_scenes * max_views_per_scene, 128), 128, 0, st>>>(
+      inv_poses, intrinsics, view_off, w.bbox, n_scenes, max_views_per_scene, threshold, vc);
+  DC_LAUNCH_CHECK();
+  if (smem > 48 * 1024)
+    DC_CUDA(cudaFuncSetAttribute(visibility_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // The per-view constants live in the constant bank (uniform operands instead of 24 shared-memory
+  // wavefronts per view and warp), refreshed per group of scenes by a device-to-device copy in
+  // stream order. A group is at most one full wave of CTAs.
+  const int64_t ctas_per_scene = dc::ceil_div<int64_t>(max_points_per_scene, kTile);
+  const int64_t group = scenes_per_group(n_scenes, max_points_per_scene, max_views_per_scene);
+  for (int s0 = 0; s0 < n_scenes; s0 += (int)group) {
+    const int ns = (int)((n_scenes - s0 < group) ? (n_scenes - s0) : group);
+    DC_CUDA(cudaMemcpyToSymbolAsync(c_views, vc + (size_t)s0 * max_views_per_scene,
+                                    sizeof(ViewConst) * (size_t)ns * max_views_per_scene, 0, cudaMemcpyDeviceToDevice, st));
+    FastParams p{points, point_off, view_off, depths, inv_poses, intrinsics, w.perm, total_points, s0,
+                 max_views_per_scene, height, width, (float)width, 0.5f * (float)(width - 2), 0.5f * (float)width,
+                 0.5f * (float)(height - 2), 0.5f * (float)height, (float)(width - 1), (float)(height - 1), threshold, records,
+                 any_visible};
+    dim3 grid((unsigned)ctas_per_scene, (unsigned)ns);
+    visibility_filter_kernel<<<grid, kThreads, smem, st>>>(p);
+  }
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

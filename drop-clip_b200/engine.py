@@ -342,14 +342,14 @@ class FusionEngine:
         records = torch.empty((max(words, 1), max(n, 1)), dtype=torch.int32, device=b.device)
         rank = torch.empty(max(n, 1), dtype=torch.int64, device=b.device)
         any_vis = torch.empty(max(n, 1), dtype=torch.uint8, device=b.device)
-        ws_bytes = self.lib.dc_visibility_sorted_workspace(n, b.n_scenes)
+        ws_bytes = self.lib.dc_visibility_sorted_workspace(n, b.n_scenes, max(b.n_views, default=0))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=b.device)
         with self._tick("project_visibility"):
             check(self.lib.dc_project_visibility_sorted(
                 ptr(b.points), ptr(b.off["point"]), ptr(b.off["view"]), ptr(b.depths), ptr(b.inv_poses), ptr(b.intrinsics),
                 b.n_scenes, n, max(b.n_points, default=0), max(b.n_views, default=0), b.height, b.width, float(threshold),
                 ptr(records), ptr(rank), ptr(any_vis), ptr(ws), ws_bytes, current_stream()))
-        self.launches += 6
+        self.launches += 7 + self.lib.dc_visibility_sorted_groups(b.n_scenes, max(b.n_points, default=0), max(b.n_views, default=0))
         return records, rank, any_vis[:n]
 
     def unpack_visibility(self, b: SceneBatch, records, rank, mask_dtype=torch.uint8):

@@ -96,8 +96,13 @@ DC_API int dc_project_visibility(const double* points, const int64_t* point_off,
  * dc_unpack_visibility_compact writes only the points with any_visible != 0 at their compacted
  * rank (new_index / kept_off from dc_compact_scan, out_off = prefix of V_s * N'_s), i.e. the mask
  * fuse_obj_prior returns (utils/feature_fusion.py:277-281) without materialising the full one.
- * workspace: dc_visibility_sorted_workspace(total_points, n_scenes) bytes. */
-DC_API size_t dc_visibility_sorted_workspace(int64_t total_points, int n_scenes);
+ * The kernel decides each (point, view) pair from an fp32 evaluation with a proven error bound and
+ * re-evaluates the undecided ones (~0.2 %) with the literal fp64 sequence, so results stay bit-identical.
+ * Limits: at most 819 views per scene, height * width <= 2^23.
+ * workspace: dc_visibility_sorted_workspace(total_points, n_scenes, max_views_per_scene) bytes. */
+DC_API size_t dc_visibility_sorted_workspace(int64_t total_points, int n_scenes, int max_views_per_scene);
+/* number of filter-kernel launches dc_project_visibility_sorted issues for these extents (launch accounting) */
+DC_API int dc_visibility_sorted_groups(int n_scenes, int64_t max_points_per_scene, int max_views_per_scene);
 DC_API int dc_project_visibility_sorted(const double* points, const int64_t* point_off, const int64_t* view_off,
                                  const float* depths, const float* inv_poses, const double* intrinsics,
                                  int n_scenes, int64_t total_points, int64_t max_points_per_scene,

@@ -32,7 +32,10 @@ def mvff(sc, **kw):
     return MultiviewFeatureFusion(sc.intrinsic, image_size=(sc.intrinsic["height"], sc.intrinsic["width"]), device="cuda", **kw)
 
 
-def engine_visibility(sc, points, mask_dtype=torch.uint8, point_object=False):
+KERNELS = ["direct", "sorted"]  # literal fp64 kernel / counting-sorted fp32 filter + exact queue
+
+
+def engine_visibility(sc, points, mask_dtype=torch.uint8, point_object=False, kernel="direct", threshold=0.05):
     """Visibility through the engine with the inverse poses stored in the golden file (so the
     result does not depend on this host's LAPACK)."""
     from dropclip_b200.engine import FusionEngine, SceneBatch
@@ -40,7 +43,12 @@ def engine_visibility(sc, points, mask_dtype=torch.uint8, point_object=False):
     scene = {"points": points, "depths": sc.depths, "camera_poses": sc.camera_poses, "intrinsic": sc.intrinsic,
              "seg_masks": sc.seg_masks}
     b = SceneBatch.from_host([scene], "cuda", inv_poses=[sc.inv_poses])
-    mask, anyv, pobj = eng.visibility(b, 0.05, mask_dtype, point_object)
+    if kernel == "sorted":
+        assert not point_object
+        records, rank, anyv = eng.visibility_sorted(b, threshold)
+        mask, pobj = eng.unpack_visibility(b, records, rank, mask_dtype), None
+    else:
+        mask, anyv, pobj = eng.visibility(b, threshold, mask_dtype, point_object)
     torch.cuda.synchronize()
     V, N = len(sc.depths), points.shape[0]
     return mask.view(V, N).cpu().numpy(), anyv.cpu().numpy(), None if pobj is None else pobj.view(V, N).cpu().numpy()
@@ -48,15 +56,16 @@ def engine_visibility(sc, points, mask_dtype=torch.uint8, point_object=False):
 
 @pytest.mark.parametrize("name", FUSE)
 @pytest.mark.parametrize("mask_dtype", [torch.uint8, torch.int64])
-def test_visibility_bit_exact_vs_reference_golden(name, mask_dtype):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_visibility_bit_exact_vs_reference_golden(name, mask_dtype, kernel):
     z = gio.load(name)
     sc = gio.scene_of(z)
-    m, anyv, _ = engine_visibility(sc, sc.points, mask_dtype)
+    m, anyv, _ = engine_visibility(sc, sc.points, mask_dtype, kernel=kernel)
     want = gio.unpack(z["vis"], sc.n_points)
     assert np.array_equal(m.astype(np.uint8), want)
     assert np.array_equal(anyv.astype(bool), want.sum(0) > 0)
     adv = z["adv_points"]
-    m, _, _ = engine_visibility(sc, adv, mask_dtype)
+    m, _, _ = engine_visibility(sc, adv, mask_dtype, kernel=kernel)
     assert np.array_equal(m.astype(np.uint8), gio.unpack(z["adv_vis"], adv.shape[0]))
 
 
@@ -77,7 +86,8 @@ def test_visibility_and_object_lookup_vs_c_oracle_fresh_scene():
         assert np.array_equal(pobj[v].astype(np.int64), want_obj)
 
 
-def test_visibility_points_on_pixel_corners_take_the_exact_path():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_visibility_points_on_pixel_corners_take_the_exact_path(kernel):
     """Points back-projected from integer pixel corners project to (almost) exact integers - the
     case where the shared-reciprocal fast path must defer to the IEEE divisions."""
     from oracle import c_oracle
@@ -98,13 +108,78 @@ def test_visibility_points_on_pixel_corners_take_the_exact_path():
         pts.append(P[:3, 3] + xc[:, None] * P[:3, 0] - yc[:, None] * P[:3, 1] - z[:, None] * P[:3, 2])
     pts = np.concatenate(pts)
     sc.inv_poses = [np.linalg.inv(p) for p in sc.camera_poses]
-    m, _, _ = engine_visibility(sc, pts, torch.uint8)
+    m, _, _ = engine_visibility(sc, pts, torch.uint8, kernel=kernel)
     want = c_oracle.visibility_mask(pts, sc.depths, None, intrinsic_matrix(sc.intrinsic), inv_poses=sc.inv_poses)
     assert np.array_equal(m.astype(np.int64), want)
     assert want.sum() > 1000
 
 
-def test_visibility_general_intrinsics_and_huge_values():
+@pytest.mark.parametrize("threshold", [0.05, 0.0, 1e-7, -1.0, 3.0, float("nan")])
+def test_sorted_filter_depth_threshold_edges_vs_c_oracle(threshold):
+    """Points placed at |depth - z| = threshold * (1 +- tiny) and exactly on the sensor surface, NaN / inf
+    depth pixels, for several thresholds: the fp32 filter must hand every close call to the exact path."""
+    from oracle import c_oracle
+    from dropclip_b200.scenes import small_scene
+    from dropclip_b200.engine import intrinsic_matrix
+    H, W = 120, 161  # odd width
+    sc = small_scene(77, n_views=4, n_points=100, n_objects=5, height=H, width=W)
+    rng = np.random.default_rng(5)
+    thr = 0.05 if threshold != threshold else abs(threshold)
+    pts = []
+    for v in range(sc.n_views):
+        P = sc.camera_poses[v].astype(np.float64)
+        us = rng.uniform(-2, W + 1, size=6000)
+        vs = rng.uniform(-2, H + 1, size=6000)
+        d = sc.depths[v][np.clip(vs, 0, H - 1).astype(int), np.clip(us, 0, W - 1).astype(int)].astype(np.float64)
+        off = rng.choice([0.0, thr, -thr, thr * (1 + 1e-9), thr * (1 - 1e-9), thr + 1e-6, thr - 1e-6, thr + 1e-4, -thr - 1e-7,
+                          thr * (1 + 1e-15)], size=d.shape)
+        z = d + off
+        xc = (us - sc.intrinsic["cx"]) / sc.intrinsic["fx"] * z
+        yc = (vs - sc.intrinsic["cy"]) / sc.intrinsic["fy"] * z
+        pts.append(P[:3, 3] + xc[:, None] * P[:3, 0] - yc[:, None] * P[:3, 1] - z[:, None] * P[:3, 2])
+        sc.depths[v] = sc.depths[v].copy()
+    sc.depths[1][::7, ::5] = np.nan
+    sc.depths[2][::9, ::4] = np.inf
+    pts = np.concatenate(pts)
+    sc.inv_poses = [np.linalg.inv(p) for p in sc.camera_poses]
+    m, _, _ = engine_visibility(sc, pts, torch.uint8, kernel="sorted", threshold=threshold)
+    with np.errstate(all="ignore"):
+        want = c_oracle.visibility_mask(pts, sc.depths, None, intrinsic_matrix(sc.intrinsic), inv_poses=sc.inv_poses,
+                                        threshold=threshold)
+    assert np.array_equal(m.astype(np.int64), want)
+    if threshold in (0.05, 3.0):
+        assert want.sum() > 1000
+
+
+@pytest.mark.parametrize("scale", [1e-3, 1.0, 1e4, 1e12])
+def test_sorted_filter_scaled_worlds_vs_c_oracle(scale):
+    """The filter's error bound scales with the scene's coordinate magnitudes: tiny, metric and huge
+    worlds (points, camera translations and depth scaled together), cameras inside the cloud."""
+    from oracle import c_oracle
+    from dropclip_b200.scenes import small_scene
+    from dropclip_b200.engine import intrinsic_matrix
+    sc = small_scene(55, n_views=5, n_points=20000, n_objects=6, height=120, width=160)
+    pts = sc.points * scale
+    poses = []
+    for v, Pm in enumerate(sc.camera_poses):
+        Pm = Pm.astype(np.float64).copy()
+        Pm[:3, 3] *= scale
+        if v == 4:
+            Pm[:3, 3] = pts[17]  # a camera sitting on a scene point: z ~ 0 for it and its neighbours
+        poses.append(Pm.astype(np.float32))
+        sc.depths[v] = (sc.depths[v].astype(np.float64) * scale).astype(np.float32)
+    sc.camera_poses = poses
+    sc.inv_poses = [np.linalg.inv(p) for p in poses]
+    thr = 0.05 * scale
+    m, _, _ = engine_visibility(sc, pts, torch.uint8, kernel="sorted", threshold=thr)
+    with np.errstate(all="ignore"):
+        want = c_oracle.visibility_mask(pts, sc.depths, None, intrinsic_matrix(sc.intrinsic), inv_poses=sc.inv_poses,
+                                        threshold=thr)
+    assert np.array_equal(m.astype(np.int64), want)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_visibility_general_intrinsics_and_huge_values(kernel):
     """Non-pinhole K (skew, non-unit K[2,2]) and operands >= 1e100 use the literal path."""
     from oracle import c_oracle
     from dropclip_b200 import _lib
@@ -119,7 +194,11 @@ def test_visibility_general_intrinsics_and_huge_values():
     b = SceneBatch.from_host([{"points": pts, "depths": sc.depths, "camera_poses": sc.camera_poses,
                                "intrinsic": sc.intrinsic}], "cuda", inv_poses=[inv])
     b.intrinsics = torch.from_numpy(K.reshape(1, 9)).cuda()
-    mask, _, _ = eng.visibility(b, 0.05, torch.uint8)
+    if kernel == "sorted":
+        records, rank, _ = eng.visibility_sorted(b, 0.05)
+        mask = eng.unpack_visibility(b, records, rank, torch.uint8)
+    else:
+        mask, _, _ = eng.visibility(b, 0.05, torch.uint8)
     with np.errstate(all="ignore"):
         want = c_oracle.visibility_mask(pts, sc.depths, None, K, inv_poses=inv)
     assert np.array_equal(mask.view(3, -1).cpu().numpy().astype(np.int64), want)
