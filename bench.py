@@ -265,12 +265,14 @@ def run_ours(args):
                 outs.append((f.cpu(), w.cpu(), vis))  # device->host read of the step's results
             return outs
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            e2e_step()
+        outs = None
+        for _ in range(max(3, args.warmup)):
+            outs = e2e_step()  # results stay referenced across steps, exactly like in the timed loop (pinned-buffer reuse)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         n_e2e = max(2, min(args.steps, 5))
+        up0 = M._staging.bytes_uploaded
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             outs = e2e_step()
@@ -278,14 +280,36 @@ def run_ours(args):
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        s0 = host[0]
-        h2d = sum(sum(d.nbytes for d in s.depths) + sum(m.nbytes for m in s.seg_masks) + s.points.nbytes + s.labels.nbytes
-                  + sum(f.numel() * f.element_size() for f in s.mv_features) + s.query_embeddings.numel() * 4
-                  + len(s.depths) * 64 for s in host)
-        d2h = sum(f.numel() * 4 + w.numel() * 4 + vis.numel() for f, w, vis in outs) + sum(s.points.shape[0] for s in host)
+        h2d = (M._staging.bytes_uploaded - up0) // n_e2e  # bytes that crossed PCIe (instance maps travel as uint8)
+        host_in = sum(sum(d.nbytes for d in s.depths) + sum(m.nbytes for m in s.seg_masks) + s.points.nbytes + s.labels.nbytes
+                      + s.colors.nbytes + sum(f.numel() * f.element_size() for f in s.mv_features)
+                      + s.query_embeddings.numel() * 4 + len(s.depths) * 64 for s in host)
+        d2h = sum(f.numel() * 4 + w.numel() * 4 + vis.numel() * 8 + vis.shape[1] * (24 + 24 + 8) for f, w, vis in outs) \
+            + sum(s.points.shape[0] * 8 for s in host)
+        # same scenes through the overlapped scene loop (staging of scene i+1 under the fusion of scene i)
+        def many_step():
+            return [(f.cpu(), w.cpu(), vis) for (f, w, vis), _ in M.fuse_many(
+                [(s.points, s.colors, s.labels, s.depths, s.seg_masks, s.camera_poses, s.mv_features, s.query_embeddings)
+                 for s in host], return_obj=True, device=dev)]
+        for _ in range(3):
+            outs_many = many_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t1 = time.perf_counter()
+        for _ in range(n_e2e):
+            outs_many = many_step()
+        torch.cuda.synchronize()
+        dt_many = torch.tensor([time.perf_counter() - t1], device=dev)
+        if world > 1:
+            dist.all_reduce(dt_many, op=dist.ReduceOp.MAX)
+        e2e_pipelined = {"value": world * args.e2e_scenes * n_e2e / float(dt_many.item()), "unit": "scenes/s",
+                         "api": "MultiviewFeatureFusion.fuse_many(iterable of fuse() argument tuples)"}
         e2e = {"value": world * args.e2e_scenes * n_e2e / float(dt.item()), "unit": "scenes/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "scenes_per_step": args.e2e_scenes,
-               "api": "MultiviewFeatureFusion.fuse(host numpy inputs, return_obj=True)", "steps": n_e2e}
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "host_input_bytes_per_step": int(host_in),
+               "scenes_per_step": args.e2e_scenes,
+               "api": "MultiviewFeatureFusion.fuse(host numpy inputs, return_obj=True), one call per scene like "
+                      "tools/preprocess_data.py:268", "steps": n_e2e, "pipelined": e2e_pipelined}
         del host, M
 
     # ---- CPU baseline (rank 0, N=1): one scene of the workload through the oracle port

@@ -59,6 +59,8 @@ SIGNATURES = {
     "dc_unique_max_pool": (c_int, [P, P, c_int, c_int, c_int64, P, P, P, P, c_size_t, P]),
     "dc_voxel_down_mean": (c_int, [P, c_int64, c_double, P, P, P, P, c_size_t, P]),
     "dc_nearest_index": (c_int, [P, c_int64, P, c_int64, P, P, P]),
+    "dc_host_gather_copy": (c_int, [P, c_int64, c_int64, P, c_int]),
+    "dc_host_gather_narrow_i64_u8": (c_int, [P, c_int64, c_int64, P, c_int, POINTER(c_int)]),
 }
 
 _lib = None

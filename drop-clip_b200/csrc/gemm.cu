@@ -89,10 +89,106 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(T* __restrict__ x, i
   }
 }
 
+// Same arithmetic, organised for bandwidth: a warp keeps its whole row in registers (128-bit loads,
+// kChunks x 8 fp16 or kChunks x 4 fp32 per lane), reduces, scales and writes it back once. Used when
+// dim == 32 * kChunks * (16 / sizeof(T)) and the rows are 16-byte aligned (dim = 768: fp16 3 chunks,
+// fp32 6 chunks). The generic kernel above reads the row twice with 2- or 4-byte accesses.
+template <typename T, bool kInPlace, int kChunks>
+__global__ void __launch_bounds__(256) row_normalize_vec_kernel(T* __restrict__ x, int64_t n_rows, int normalize,
+                                                                __half* __restrict__ hi, __half* __restrict__ lo) {
+  constexpr int kPer = 16 / (int)sizeof(T);       // elements per 128-bit access
+  constexpr int kDim = 32 * kChunks * kPer;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  T* xr = x + row * kDim;
+  float v[kChunks][kPer];
+#pragma unroll
+  for (int k = 0; k < kChunks; ++k) {
+    const int4 raw = dc::ld_stream(reinterpret_cast<const int4*>(xr) + k * 32 + lane);
+    if (sizeof(T) == 2) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        v[k][2 * j] = f.x;
+        v[k][2 * j + 1] = f.y;
+      }
+    } else {
+      const float* f = reinterpret_cast<const float*>(&raw);
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) v[k][j] = f[j];
+    }
+  }
+  if (normalize) {
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k)
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) ss = fmaf(v[k][j], v[k][j], ss);
+    ss = dc::warp_sum(ss);
+    float nrm = sqrtf(ss);
+    if (sizeof(T) == 2) nrm = __half2float(__float2half_rn(nrm));
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k)
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        float q = v[k][j] / nrm;  // IEEE division, like torch
+        if (sizeof(T) == 2) q = __half2float(__float2half_rn(q));
+        v[k][j] = q;
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < kChunks; ++k) {
+    if (sizeof(T) == 2) {
+      int4 packed;
+      __half2* h2 = reinterpret_cast<__half2*>(&packed);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(v[k][2 * j], v[k][2 * j + 1]);
+      if (normalize && kInPlace) dc::st_stream(reinterpret_cast<int4*>(xr) + k * 32 + lane, packed);
+      if (hi) dc::st_stream(reinterpret_cast<int4*>(hi + row * kDim) + k * 32 + lane, packed);
+    } else {
+      if (normalize && kInPlace) {
+        int4 packed;
+        float* f = reinterpret_cast<float*>(&packed);
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) f[j] = v[k][j];
+        dc::st_stream(reinterpret_cast<int4*>(xr) + k * 32 + lane, packed);
+      }
+      if (hi) {
+        // 4 fp32 -> 4 fp16 (+ 4 fp16 residuals): 8-byte stores, still fully coalesced per warp
+        __half2 h[2], l[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          h[j] = __floats2half2_rn(v[k][2 * j], v[k][2 * j + 1]);
+          const float2 back = __half22float2(h[j]);
+          l[j] = __floats2half2_rn(v[k][2 * j] - back.x, v[k][2 * j + 1] - back.y);
+        }
+        *reinterpret_cast<uint2*>(hi + row * kDim + (k * 32 + lane) * 4) = *reinterpret_cast<uint2*>(h);
+        if (lo) *reinterpret_cast<uint2*>(lo + row * kDim + (k * 32 + lane) * 4) = *reinterpret_cast<uint2*>(l);
+      }
+    }
+  }
+}
+
 int launch_row_normalize(void* x, int dtype, int64_t n_rows, int dim, int normalize, bool in_place, void* hi, void* lo,
                          cudaStream_t st) {
   if (n_rows <= 0) return DC_OK;
   const unsigned grid = (unsigned)dc::ceil_div<int64_t>(n_rows, 8);
+  const bool aligned = ((uintptr_t)x & 15) == 0 && ((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0;
+  if (aligned && dim == 768) {  // the CLIP ViT-L/14 width of every caller (models/features/clip); other widths: generic kernel
+    __half* h = (__half*)hi;
+    __half* l = (__half*)lo;
+    if (dtype == DC_F16) {
+      if (in_place) row_normalize_vec_kernel<__half, true, 3><<<grid, 256, 0, st>>>((__half*)x, n_rows, normalize, h, nullptr);
+      else row_normalize_vec_kernel<__half, false, 3><<<grid, 256, 0, st>>>((__half*)x, n_rows, normalize, h, nullptr);
+    } else {
+      if (in_place) row_normalize_vec_kernel<float, true, 6><<<grid, 256, 0, st>>>((float*)x, n_rows, normalize, h, l);
+      else row_normalize_vec_kernel<float, false, 6><<<grid, 256, 0, st>>>((float*)x, n_rows, normalize, h, l);
+    }
+    DC_LAUNCH_CHECK();
+    return DC_OK;
+  }
   if (dtype == DC_F16) {
     if (in_place) row_normalize_kernel<__half, true><<<grid, 256, 0, st>>>((__half*)x, n_rows, dim, normalize, (__half*)hi, nullptr);
     else row_normalize_kernel<__half, false><<<grid, 256, 0, st>>>((__half*)x, n_rows, dim, normalize, (__half*)hi, nullptr);
@@ -122,8 +218,8 @@ struct EpiStore {
         if (i < n) dst[i] = v[i];
     }
   }
-  __device__ __forceinline__ void finish_row(const Tile&, int) {}
-  __device__ __forceinline__ void finish_warp() {}
+  __device__ __forceinline__ void begin(const Tile&, int, float) {}
+  __device__ __forceinline__ void finish(const Tile&, int, int, int, float*) {}
 };
 
 __device__ __forceinline__ void atomic_min_f(float* a, float v) {
@@ -137,8 +233,19 @@ __device__ __forceinline__ void atomic_max_f(float* a, float v) {
   else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
 }
 
-// Grounding epilogue. Every thread owns one point (row); the prompt axis is walked in 32-column
-// chunks, so the N x P similarity matrix never leaves the SM unless mode == RAW.
+// Grounding epilogue. A thread owns one point (row) and one half of the prompt axis, walked in
+// 32-column chunks, so the N x P similarity matrix never leaves the SM unless mode == RAW. The two
+// halves of a row meet in shared memory (finish).
+//   paired:  out = 1 / (Nneg + sum_neg exp((neg - pos) / T))   (closed form of models/similarity.py:51-61)
+//   argmax:  out = pos - mean(neg), pred = (pos >= max(neg))    (:91-101)
+// exp is evaluated as ex2((v - pos) * log2(e) / T) with four independent partial sums; a result below
+// 2^-126 flushes to zero and one above 2^128 gives inf -> out = 0, the limits of the closed form.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct EpiGround {
   int mode;
   int n_prompts;
@@ -148,68 +255,103 @@ struct EpiGround {
   uint8_t* pred;
   float* minmax;  // [0] min(out) [1] max(out) [2] min(raw) [3] max(raw)
   // per-thread running state
-  float pos, acc, neg_max, raw_min, raw_max;
-  float out_min, out_max;
-  bool have;
+  float pos, scale, bias, acc[4], neg_max, raw_min, raw_max;
 
-  __device__ __forceinline__ void row(const Tile& t, int r, int c0, const float (&v)[32]) {
-    if (c0 == 0) {
-      pos = v[0];
-      acc = 0.f;
-      neg_max = -INFINITY;
-      raw_min = INFINITY;
-      raw_max = -INFINITY;
-    }
-    if (r >= t.rows) return;
-    const int n = min(32, n_prompts - c0);
-    if (mode == DC_GROUND_RAW) {
-      float* dst = out + (int64_t)(t.a_row + r) * out_ld + c0;
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < n) {
-          dst[i] = v[i];
-          raw_min = fminf(raw_min, v[i]);
-          raw_max = fmaxf(raw_max, v[i]);
-        }
-      return;
-    }
+  __device__ __forceinline__ void begin(const Tile&, int, float col0) {
+    pos = col0;
+    scale = inv_temp * 1.4426950408889634f;  // log2(e) / T
+    bias = -pos * scale;
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    neg_max = -INFINITY;
+    raw_min = INFINITY;
+    raw_max = -INFINITY;
+  }
+
+  template <bool kMasked>
+  __device__ __forceinline__ void chunk(int c0, const float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      if (i < n) {
+      const bool valid = !kMasked || (c0 + i < n_prompts);
+      const bool neg = !kMasked || (valid && c0 + i > 0);
+      if (valid) {
         raw_min = fminf(raw_min, v[i]);
         raw_max = fmaxf(raw_max, v[i]);
-        if (c0 + i > 0) {
-          if (mode == DC_GROUND_PAIRED) acc += __expf((v[i] - pos) * inv_temp);
-          else { acc += v[i]; neg_max = fmaxf(neg_max, v[i]); }
-        }
+      }
+      if (neg) {
+        if (mode == DC_GROUND_PAIRED) acc[i & 3] += ex2_approx(fmaf(v[i], scale, bias));
+        else { acc[i & 3] += v[i]; neg_max = fmaxf(neg_max, v[i]); }
       }
     }
   }
-  __device__ __forceinline__ void finish_row(const Tile& t, int r) {
-    have = r < t.rows;
-    if (!have) return;
-    const int64_t gr = (int64_t)t.a_row + r;
-    float o;
+
+  __device__ __forceinline__ void row(const Tile& t, int r, int c0, const float (&v)[32]) {
+    if (r >= t.rows) return;
     if (mode == DC_GROUND_RAW) {
-      out_min = raw_min;
-      out_max = raw_max;
+      float* dst = out + (int64_t)(t.a_row + r) * out_ld + c0;
+      const int n = min(32, n_prompts - c0);
+      if (n == 32 && (out_ld & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          raw_min = fminf(raw_min, v[i]);
+          raw_max = fmaxf(raw_max, v[i]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < n) {
+            dst[i] = v[i];
+            raw_min = fminf(raw_min, v[i]);
+            raw_max = fmaxf(raw_max, v[i]);
+          }
+      }
       return;
     }
-    const float n_neg = (float)(n_prompts - 1);
-    if (mode == DC_GROUND_PAIRED) {
-      o = 1.f / (n_neg + acc);
-      if (o != o) o = 0.f;  // nan_to_num
-    } else {
-      o = pos - acc / n_neg;
-      pred[gr] = (pos >= neg_max) ? 1 : 0;  // argmax == 0 (first index wins ties)
-    }
-    out[gr] = o;
-    out_min = o;
-    out_max = o;
+    if (c0 > 0 && c0 + 32 <= n_prompts) chunk<false>(c0, v);  // interior chunk: no masks
+    else chunk<true>(c0, v);                                  // holds the positive column or the ragged end
   }
-  __device__ __forceinline__ void finish_warp() {
-    float a = have ? out_min : INFINITY, b = have ? out_max : -INFINITY;
-    float c = have ? raw_min : INFINITY, d = have ? raw_max : -INFINITY;
+
+  __device__ __forceinline__ void finish(const Tile& t, int r, int half, int n_halves, float* scratch) {
+    float sum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    if (n_halves == 2) {
+      // half 1 hands its partials to half 0 through shared memory; barrier 1 is private to the 8 epilogue warps
+      float* slot = scratch + r * 4;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done with the scratch
+      if (half == 1) {
+        slot[0] = sum;
+        slot[1] = neg_max;
+        slot[2] = raw_min;
+        slot[3] = raw_max;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 1) return;
+      sum += slot[0];
+      neg_max = fmaxf(neg_max, slot[1]);
+      raw_min = fminf(raw_min, slot[2]);
+      raw_max = fmaxf(raw_max, slot[3]);
+    }
+    const bool have = r < t.rows;
+    float o = 0.f;
+    if (have && mode != DC_GROUND_RAW) {
+      const int64_t gr = (int64_t)t.a_row + r;
+      const float n_neg = (float)(n_prompts - 1);
+      if (mode == DC_GROUND_PAIRED) {
+        o = 1.f / (n_neg + sum);
+        if (o != o) o = 0.f;  // nan_to_num
+      } else {
+        o = pos - sum / n_neg;
+        pred[gr] = (pos >= neg_max) ? 1 : 0;  // argmax == 0 (first index wins ties)
+      }
+      out[gr] = o;
+    }
+    float a = INFINITY, b = -INFINITY, c = INFINITY, d = -INFINITY;
+    if (have) {
+      a = (mode == DC_GROUND_RAW) ? raw_min : o;
+      b = (mode == DC_GROUND_RAW) ? raw_max : o;
+      c = raw_min;
+      d = raw_max;
+    }
     a = dc::warp_min(a); b = dc::warp_max(b); c = dc::warp_min(c); d = dc::warp_max(d);
     if ((threadIdx.x & 31) == 0) {
       if (a != INFINITY) atomic_min_f(minmax + 0, a);

@@ -5,9 +5,17 @@
 // lo.hi into the same accumulator, which restores ~22 bits of operand precision while staying on
 // the full-rate kind::f16 tensor path.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> global). Three pipelines: smem full/empty ring
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (TMEM -> registers -> global). Three pipelines: smem full/empty ring
 // (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue), persistent tile loop.
+//
+// Epilogue layout: a warp may only read the TMEM lane quarter (warp % 4), so the eight epilogue
+// warps form two groups of four; group h handles the column half [h * BN/2, (h+1) * BN/2) of every
+// row (for BN < 64 only group 0 works). A thread owns one row and walks its columns in 32-wide
+// chunks with the tcgen05.ld of chunk c+1 in flight while chunk c is processed. Measured on the
+// grounding shape (profiles/r01_ncu_gemm_ground_v1_raw.csv): with four single-row warps and a
+// blocking load per chunk the tensor pipe was 18 % busy and the kernel spent its time in the
+// epilogue's dependent instruction chains (issue slots 18 % used).
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -18,7 +26,8 @@ namespace gemm {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 fp16 = 128 bytes = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
+constexpr int kEpilogueWarps = 8;
 constexpr int kEpilogueWarp0 = 2;
 
 struct Tile {
@@ -44,7 +53,7 @@ struct Config {
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator buffers
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBlockM * 8 * 4 /*epilogue scratch*/;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two");
 };
@@ -59,10 +68,12 @@ __device__ __forceinline__ Tile fetch_tile(const Params& p, int t) {
   return Tile{(int)r0, 0, (int)(left < kBlockM ? left : kBlockM), p.n_cols};
 }
 
-// Epilogue functor contract:
-//   struct Epi { __device__ void row(const Tile&, int row_in_tile, int col0, const float (&v)[32]);   // 32 columns
-//                __device__ void finish_row(const Tile&, int row_in_tile);  // after the last chunk
-//                __device__ void finish_warp(); }                           // once per tile per warp
+// Epilogue functor contract (one instance per thread, copied from the kernel argument):
+//   void begin(const Tile&, int row_in_tile, float col0_value);        // value of column 0 of this row
+//   void row(const Tile&, int row_in_tile, int col0, const float (&v)[32]);   // 32 columns starting at col0
+//   void finish(const Tile&, int row_in_tile, int half, int n_halves, float* scratch);
+//        // after the last chunk; `scratch` = kBlockM * 8 floats of shared memory for combining the two
+//        // column halves of a row (all epilogue threads of the active groups call finish together)
 template <int BN, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -79,6 +90,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_scratch = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);  // [kBlockM * 8]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,7 +108,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       umma::mbar_init(tmem_full + a, 1);
-      umma::mbar_init(tmem_empty + a, 4);  // one arrival per epilogue warp
+      umma::mbar_init(tmem_empty + a, (BN >= 64) ? 8 : 4);  // one arrival per active epilogue warp
     }
     umma::fence_barrier_init();
   }
@@ -161,32 +173,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     }
   } else {
     // ===================== epilogue warps =====================
+    constexpr int kHalves = (BN >= 64) ? 2 : 1;
+    constexpr int kHalfCols = BN / kHalves;
+    constexpr int kChunks = kHalfCols / 32;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (warp - kEpilogueWarp0) >> 2;
     const int row_in_tile = quarter * 32 + lane;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const Tile tile = fetch_tile(p, t);
-      umma::mbar_wait(tmem_full + acc, acc_phase);
-      umma::fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN && c0 < tile.cols; c0 += 32) {  // warp-uniform bounds
-        uint32_t r[32];
+    if (half < kHalves) {
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const Tile tile = fetch_tile(p, t);
+        umma::mbar_wait(tmem_full + acc, acc_phase);
+        umma::fence_after_sync();
+        const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+        const uint32_t taddr = tacc + (uint32_t)(half * kHalfCols);
+        const int c_base = half * kHalfCols;
+        uint32_t ra[32], rb[32], r0;
         __syncwarp();
-        umma::tmem_ld_32x32(taddr + (uint32_t)c0, r);
+        umma::tmem_ld_32x32_x1(tacc, r0);
+        umma::tmem_ld_32x32(taddr, ra);
         umma::tmem_ld_wait();
-        float v[32];
+        epi.begin(tile, row_in_tile, __uint_as_float(r0));
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epi.row(tile, row_in_tile, c0, v);
+        for (int c = 0; c < kChunks; ++c) {
+          uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+          uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
+          const bool more = (c + 1 < kChunks) && (c_base + (c + 1) * 32 < tile.cols);  // warp-uniform
+          if (more) umma::tmem_ld_32x32(taddr + (uint32_t)((c + 1) * 32), nxt);
+          if (c_base + c * 32 < tile.cols) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cur[i]);
+            epi.row(tile, row_in_tile, c_base + c * 32, v);
+          }
+          if (c + 1 < kChunks) umma::tmem_ld_wait();
+        }
+        umma::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(tmem_empty + acc);  // TMEM buffer may be overwritten
+        epi.finish(tile, row_in_tile, half, kHalves, epi_scratch);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      umma::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(tmem_empty + acc);  // TMEM buffer may be overwritten
-      epi.finish_row(tile, row_in_tile);
-      epi.finish_warp();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 

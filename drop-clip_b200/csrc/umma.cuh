@@ -93,6 +93,10 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+// one column: thread (= lane = row) gets a single fp32
+__device__ __forceinline__ void tmem_ld_32x32_x1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ descriptors

@@ -12,12 +12,17 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
+import ctypes
+import os
+
 import numpy as np
 import torch
 
 from . import _lib
 from ._lib import check, current_stream, ptr
 
+_TORCH_TO_NP = {torch.float32: np.dtype(np.float32), torch.float64: np.dtype(np.float64), torch.int64: np.dtype(np.int64),
+                torch.int32: np.dtype(np.int32), torch.uint8: np.dtype(np.uint8), torch.float16: np.dtype(np.float16)}
 SIM_KERNELS = {None: _lib.DC_SIM_NONE, "max": _lib.DC_SIM_MAX, "mean": _lib.DC_SIM_MEAN}
 MAX_BINS = 256  # instance ids are stored as uint8 labels downstream (tools/preprocess_data.py:294)
 
@@ -100,7 +105,8 @@ class SceneBatch:
 
     @classmethod
     def from_host(cls, scenes: Sequence, device="cuda", pixel_features: bool = False,
-                  inv_poses: Optional[Sequence] = None, staging: Optional["PinnedStaging"] = None) -> "SceneBatch":
+                  inv_poses: Optional[Sequence] = None, staging: Optional["PinnedStaging"] = None,
+                  narrow_segs: bool = True) -> "SceneBatch":
         """Uploads scenes given in the reference's own containers (numpy arrays and lists, torch
         feature tensors). `scenes[i]` needs attributes/keys points, depths, camera_poses, intrinsic
         and optionally labels, seg_masks, mv_features, query_embeddings.
@@ -152,7 +158,14 @@ class SceneBatch:
                 if staging is not None:
                     tdt = {np.dtype(np.uint8): torch.uint8, np.dtype(np.int32): torch.int32,
                            np.dtype(np.int64): torch.int64}[np.dtype(dt)]
-                    b.segs = staging.upload_list(segs, tdt, (H, W))
+                    narrowed = False
+                    if narrow_segs and tdt == torch.int64 and all(
+                            isinstance(m, np.ndarray) and m.dtype == np.int64 and m.flags.c_contiguous for m in segs):
+                        # instance ids fit a byte in every valid input (ids index the Q <= 256 query rows, quirk
+                        # q7): ship 1 byte per pixel instead of 8; fall back to int64 if some id does not fit
+                        b.segs, narrowed = staging.upload_list(segs, tdt, (H, W), narrow_to_u8=True)
+                    if not narrowed:
+                        b.segs = staging.upload_list(segs, tdt, (H, W))
                 else:
                     b.segs = up(np.stack([m.astype(dt, copy=False) for m in segs]))
         if get(scenes[0], "labels") is not None:
@@ -230,31 +243,65 @@ class PinnedStaging:
         self._event = torch.cuda.Event()
         self._event.record()
 
-    def upload_list(self, arrays, dtype: torch.dtype, item_shape, group_bytes: int = 24 << 20) -> torch.Tensor:
-        """Stacks a list of equally-shaped host arrays straight into one pinned buffer (one host
-        copy per array instead of np.stack + a second copy) and uploads it group by group, so the
-        H2D copy of group g overlaps the host copy of group g+1 (both run near DRAM / PCIe speed)."""
-        n = len(arrays)
-        numel = int(np.prod(item_shape)) if len(item_shape) else 1
+    def _pinned(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
         if self._slot == len(self._bufs):
-            self._bufs.append(torch.empty(max(n * numel, 1), dtype=dtype, pin_memory=True))
+            self._bufs.append(torch.empty(max(numel, 1), dtype=dtype, pin_memory=True))
         buf = self._bufs[self._slot]
-        if buf.dtype != dtype or buf.numel() < n * numel:
-            buf = torch.empty(max(n * numel, 1), dtype=dtype, pin_memory=True)
+        if buf.dtype != dtype or buf.numel() < numel:
+            buf = torch.empty(max(numel, 1), dtype=dtype, pin_memory=True)
             self._bufs[self._slot] = buf
         self._slot += 1
+        return buf
+
+    @staticmethod
+    def _host_threads() -> int:
+        return max(1, min(16, (os.cpu_count() or 1)))
+
+    def upload_list(self, arrays, dtype: torch.dtype, item_shape, group_bytes: int = 48 << 20,
+                    narrow_to_u8: bool = False):
+        """Stacks a list of equally-shaped host arrays straight into one pinned buffer and uploads it
+        group by group, so the H2D copy of group g overlaps the host copy of group g+1. Contiguous
+        numpy arrays of the right dtype go through libdropclip's multi-threaded gather-copy (one call
+        per group); anything else through per-item tensor copies.
+
+        With `narrow_to_u8` (int64 instance maps) the values are narrowed to uint8 while being
+        staged; returns (tensor, ok) where ok is False if some value does not fit [0, 255] - the
+        caller then uploads the int64 maps as they are."""
+        n = len(arrays)
+        numel = int(np.prod(item_shape)) if len(item_shape) else 1
+        out_dtype = torch.uint8 if narrow_to_u8 else dtype
+        buf = self._pinned(n * numel, out_dtype)
         view = buf[: n * numel].view((n,) + tuple(item_shape))
-        out = torch.empty((n,) + tuple(item_shape), dtype=dtype, device=self.device)
-        per_group = max(1, group_bytes // max(1, numel * buf.element_size()))
+        out = torch.empty((n,) + tuple(item_shape), dtype=out_dtype, device=self.device)
+        np_dtype = _TORCH_TO_NP[dtype]
+        fast = all(isinstance(a, np.ndarray) and a.dtype == np_dtype and a.flags.c_contiguous and a.size == numel
+                   for a in arrays)
+        if narrow_to_u8 and not (fast and dtype == torch.int64):
+            raise ValueError("narrow_to_u8 needs contiguous int64 numpy arrays")
+        item_bytes = numel * buf.element_size()
+        per_group = max(1, group_bytes // max(1, item_bytes if not narrow_to_u8 else numel * 8))
+        lib, threads, ok = _lib.load(), self._host_threads(), True
         for g0 in range(0, n, per_group):
             g1 = min(n, g0 + per_group)
-            for i in range(g0, g1):
-                a = arrays[i]
-                t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a))
-                view[i].copy_(t.reshape(item_shape))  # converts dtype if needed
+            if fast:
+                srcs = (ctypes.c_void_p * (g1 - g0))(*[a.ctypes.data for a in arrays[g0:g1]])
+                dst = ctypes.c_void_p(view[g0].data_ptr())
+                if narrow_to_u8:
+                    bad = ctypes.c_int(0)
+                    check(lib.dc_host_gather_narrow_i64_u8(srcs, g1 - g0, numel, dst, threads, ctypes.byref(bad)))
+                    if bad.value:
+                        ok = False
+                        break
+                else:
+                    check(lib.dc_host_gather_copy(srcs, g1 - g0, item_bytes, dst, threads))
+            else:
+                for i in range(g0, g1):
+                    a = arrays[i]
+                    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a))
+                    view[i].copy_(t.reshape(item_shape))  # converts dtype if needed
             out[g0:g1].copy_(view[g0:g1], non_blocking=True)
-        self.bytes_uploaded += n * numel * buf.element_size()
-        return out
+        self.bytes_uploaded += n * item_bytes
+        return (out, ok) if narrow_to_u8 else out
 
     def download(self, t: torch.Tensor) -> torch.Tensor:
         """Async device->host copy into a reusable pinned buffer; valid until the next download()."""

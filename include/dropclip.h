@@ -318,6 +318,15 @@ DC_API int dc_voxel_down_mean(const double* points, int64_t n, double voxel_size
 DC_API int dc_nearest_index(const double* query, int64_t m, const double* ref, int64_t n, int64_t* out_index,
                      double* out_dist2, dc_stream_t stream);
 
+/* ---- host-side staging (no device work): used by the Python drop-in to fill pinned upload buffers ----
+ * dc_host_gather_copy: dst[i * item_bytes ...] = srcs[i][0 .. item_bytes) for n_items host arrays, on n_threads
+ * threads. dc_host_gather_narrow_i64_u8: same for int64 arrays of item_elems elements narrowed to uint8;
+ * *out_of_range = 1 if any value lies outside [0, 255] (the caller then ships the int64 maps unchanged, keeping
+ * the reference's error behaviour for ids >= Q, utils/feature_fusion.py:317,328-333). */
+DC_API int dc_host_gather_copy(const void* const* srcs, int64_t n_items, int64_t item_bytes, void* dst, int n_threads);
+DC_API int dc_host_gather_narrow_i64_u8(const int64_t* const* srcs, int64_t n_items, int64_t item_elems, uint8_t* dst,
+                                        int n_threads, int* out_of_range);
+
 #ifdef __cplusplus
 }
 #endif

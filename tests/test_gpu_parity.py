@@ -252,6 +252,12 @@ def test_object_level_errors_match_reference():
     with pytest.raises(IndexError):
         M.fuse(sc.points, sc.colors, sc.labels, sc.depths, bad, sc.camera_poses, sc.mv_features, sc.query_embeddings,
                return_obj=True, device="cuda")
+    for weird in (300, -1, 2 ** 40):  # ids that do not fit the uint8 staging path: int64 maps are shipped instead
+        bad = [s.copy() for s in sc.seg_masks]
+        bad[2][3, 5] = weird
+        with pytest.raises(IndexError):
+            M.fuse(sc.points, sc.colors, sc.labels, sc.depths, bad, sc.camera_poses, sc.mv_features, sc.query_embeddings,
+                   return_obj=True, device="cuda")
     short = [f[:-1] for f in sc.mv_features]  # fewer rows than ids
     with pytest.raises(IndexError):
         M.fuse(sc.points, sc.colors, sc.labels, sc.depths, sc.seg_masks, sc.camera_poses, short, sc.query_embeddings,
@@ -265,6 +271,29 @@ def test_object_level_errors_match_reference():
     with pytest.raises(RuntimeError):
         M.fuse(sc.points, sc.colors, sc.labels, sc.depths, sc.seg_masks, sc.camera_poses, sc.mv_features,
                sc.query_embeddings, return_obj=True, device="cpu")
+
+
+def test_fuse_many_equals_fuse_and_returned_row_dtypes():
+    """The overlapped scene loop yields exactly what per-scene fuse() returns; points/colors/labels come
+    back filtered in the caller's dtypes (device-side row compaction or host fallback for odd dtypes)."""
+    scs = [gio.scene_of(gio.load(n)) for n in FUSE[:2]]
+    M = mvff(scs[0], use_visibility=0, use_similarity=1, use_sim_kernel="max", use_obj_prior=1, norm_feat=False)
+    args = []
+    for i, sc in enumerate(scs * 2):
+        colors = sc.colors.astype(np.float32) if i % 2 else sc.colors
+        labels = sc.labels.astype(np.int32) if i == 1 else (sc.labels.astype(np.uint16) if i == 2 else sc.labels)
+        args.append((sc.points, colors, labels, sc.depths, sc.seg_masks, sc.camera_poses, sc.mv_features, sc.query_embeddings))
+    single = [M.fuse(*a, return_obj=True, device="cuda") for a in args]
+    many = list(M.fuse_many(args, return_obj=True, device="cuda"))
+    assert len(many) == len(single)
+    for a, (f1, w1, v1), (p1, c1, l1), ((f2, w2, v2), (p2, c2, l2)) in zip(args, [s[0] for s in single], [s[1] for s in single], many):
+        assert torch.equal(f1.cpu().nan_to_num(7.0), f2.cpu().nan_to_num(7.0)) and torch.equal(w1.cpu(), w2.cpu())
+        assert torch.equal(v1, v2) and v1.dtype == torch.int64 and v1.device.type == "cpu"
+        keep = v1.sum(0).numpy() >= 0  # all kept columns
+        for got, again, src in ((p1, p2, a[0]), (c1, c2, a[1]), (l1, l2, a[2])):
+            assert got.dtype == src.dtype and np.array_equal(got, again)
+        vis_any = M.get_visibility_mask(a[0], a[3], a[5], device="cuda").numpy().sum(0) > 0
+        assert np.array_equal(p1, a[0][vis_any]) and np.array_equal(c1, a[1][vis_any]) and np.array_equal(l1, a[2][vis_any])
 
 
 def test_object_level_batch_equals_single_scenes_and_oracle():
