@@ -173,3 +173,32 @@ def test_scene_parallel_gather_and_reduce_on_gloo_world2():
         p.join(120)
         assert p.exitcode == 0
     assert sorted(q.get(timeout=5)[0] for _ in range(2)) == [0, 1]
+
+
+def test_host_staging_helpers_copy_and_narrow():
+    """dc_host_gather_copy / dc_host_gather_narrow_i64_u8 are pure host code: exercised without a GPU."""
+    import ctypes
+    import numpy as np
+    from dropclip_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    for n_items, shape, threads in ((1, (7,), 1), (5, (33, 17), 4), (9, (480, 640), 16)):
+        numel = int(np.prod(shape))
+        arrs = [rng.random(shape, dtype=np.float32) for _ in range(n_items)]
+        dst = np.empty((n_items,) + shape, dtype=np.float32)
+        srcs = (ctypes.c_void_p * n_items)(*[a.ctypes.data for a in arrs])
+        _lib.check(lib.dc_host_gather_copy(srcs, n_items, numel * 4, ctypes.c_void_p(dst.ctypes.data), threads))
+        assert np.array_equal(dst, np.stack(arrs))
+        segs = [rng.integers(0, 256, size=shape, dtype=np.int64) for _ in range(n_items)]
+        out = np.empty((n_items,) + shape, dtype=np.uint8)
+        bad = ctypes.c_int(7)
+        srcs = (ctypes.c_void_p * n_items)(*[a.ctypes.data for a in segs])
+        _lib.check(lib.dc_host_gather_narrow_i64_u8(srcs, n_items, numel, ctypes.c_void_p(out.ctypes.data), threads,
+                                                    ctypes.byref(bad)))
+        assert bad.value == 0 and np.array_equal(out, np.stack(segs).astype(np.uint8))
+        for weird in (256, -1, 2 ** 40, -2 ** 62):
+            segs[-1].reshape(-1)[numel // 2] = weird
+            _lib.check(lib.dc_host_gather_narrow_i64_u8(srcs, n_items, numel, ctypes.c_void_p(out.ctypes.data), threads,
+                                                        ctypes.byref(bad)))
+            assert bad.value == 1
+    assert lib.dc_host_gather_copy(None, 1, 4, None, 1) != 0  # null pointers are rejected, not dereferenced
