@@ -42,15 +42,23 @@ def run(seed=1234, V=16, N=20000, jitter=0.0):
         qf = [(Pf[r, 0] * pf[:, 0] + (Pf[r, 1] * pf[:, 1] + (Pf[r, 2] * pf[:, 2] + Pf[r, 3]))).astype(f32) for r in range(3)]
         with np.errstate(all="ignore"):
             r = (f32(1) / qf[2]).astype(f32)
-        ar = np.abs(r)
         uf = (qf[0] * r).astype(f32); vf = (qf[1] * r).astype(f32)
-        rho = (f32(1.01 * Ez) * ar + f32(4 * EPS)).astype(f32)
-        hu = (f32(0.5) - f32(1.02 * Ex) * ar - np.abs(uf) * rho * f32(1.02)).astype(f32)
-        hv = (f32(0.5) - f32(1.02 * Ey) * ar - np.abs(vf) * rho * f32(1.02)).astype(f32)
-        sane = (np.abs(qf[2]) >= f32(1024 * Ez)) & (np.abs(uf) < 1e6) & (np.abs(vf) < 1e6)
+        # per-axis constants (visibility_sorted.cu: camera_prep_kernel)
+        cu, hu = (W - 1) / 2.0, (W - 1) / 2.0
+        cv, hv = (H - 1) / 2.0, (H - 1) / 2.0
+        NLu, NLv = hu + 2 + 0.0014 * W, hv + 2 + 0.0014 * H
+        Uu, Uv = cu + NLu + 1, cv + NLv + 1
+        Au = 1.02 * (Ex + 1.03 * Uu * Ez); Av = 1.02 * (Ey + 1.03 * Uv * Ez)
+        H0u = 0.499999 - 1.02 * 5 * EPS * Uu; H0v = 0.499999 - 1.02 * 5 * EPS * Uv
+        zmin = max(1024 * Ez, 4 * Ex, 4 * Ey)
+        hu_ = (f32(H0u) - f32(Au) * r).astype(f32); hv_ = (f32(H0v) - f32(Av) * r).astype(f32)
+        sane = qf[2] >= f32(zmin)
         fu = np.floor(uf); fv = np.floor(vf)
-        dec_uv = sane & (np.abs(uf - fu - f32(0.5)) < hu) & (np.abs(vf - fv - f32(0.5)) < hv)
-        in_f = (fu >= -1) & (fu <= W - 1) & (fv >= -1) & (fv <= H - 1)
+        gu = ((uf - np.abs(fu)) - f32(0.5)).astype(f32); gv = ((vf - np.abs(fv)) - f32(0.5)).astype(f32)
+        au = np.abs(fu - f32(cu)); av = np.abs(fv - f32(cv))
+        notnear = (au > f32(NLu)) | (av > f32(NLv))
+        dec_uv = sane & (notnear | ((np.abs(gu) < hu_) & (np.abs(gv) < hv_)))
+        in_f = (au <= f32(hu)) & (av <= f32(hv))
         pu_f = np.clip(fu, 0, W - 1).astype(np.int64); pv_f = np.clip(fv, 0, H - 1).astype(np.int64)
         df = sc.depths[v][pv_f, pu_f]
         delta = np.abs(df - qf[2]).astype(f32)

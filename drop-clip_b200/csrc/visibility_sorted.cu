@@ -191,22 +191,34 @@ __global__ void __launch_bounds__(kThreads) cell_scatter_kernel(const double* __
 //   q~_r = fp32 dot(P~_r, [p~;1]).  Rounding P and p to fp32 costs 2 eps per product, the chain at
 //   most 5 more roundings, the reference's own fp64 roundings ~10 u:  |q~_r - q_r| <= E_r :=
 //   8 eps * (sum_j |P_rj| * B_j + |P_r3|), B = per-scene bound on |coordinate| (from the bbox pass).
-//   r~ = rcp.approx(q~_z) (1 ulp) = (1 + eta) / q_z with |eta| <= rho := 1.03 E_z |r~| + 5 eps,
-//   valid while |q~_z| >= 1024 E_z.   u~ = q~_x * r~  =>
-//   |u~ - u| <= e_u := 1.02 (|u~| rho + E_x |r~|)            (same for v with E_y).
-//   The pair's pixel is decided when the fractional part of u~ and of v~ is farther than e from 0
-//   and 1 (so no integer lies between u~ and the reference's correctly rounded quotient); then
-//   floor(u_ref) = floor(u~), the reference's "trunc toward zero into [0, W)" test is
-//   -1 <= floor <= W-1 and its pixel is max(floor, 0)  (quirk q1: u in (-1, 0) lands on column 0).
+//   r~ = rcp.approx(q~_z) (1 ulp) = (1 + eta) / q_z with |eta| <= rho := 1.03 E_z r~ + 5 eps, valid while
+//   q~_z >= zmin := max(1024 E_z, 4 E_x, 4 E_y)  (points behind or within ~2 cm of the camera plane take
+//   the exact path; then rho <= 1.01e-3 and E_x r~ <= 0.26).   u~ = q~_x * r~  =>
+//   |u~ - u| <= 1.02 (|u~| rho + E_x r~)                     (same for v with E_y).
+//   With f = floor(u~) (exact, by the 1.5 * 2^23 trick) and c = (W - 1) / 2 a pair is, per axis,
+//     "not near"  |f - c| > NL := c + 2 + 0.0014 W : the true u lies outside [-1, W) whatever the error
+//                 (relative part <= 1.3e-3 |u~|, additive part <= 0.26) -> decided, outside;
+//     otherwise |u~| <= U := c + NL + 1 and the bound becomes linear in r~:
+//                 e_u = A_u r~ + B_u,  A_u = 1.02 (E_x + 1.03 U E_z),  B_u = 1.02 * 5 eps * U.
+//   The pixel is decided when the fractional part t = u~ - |f| lies in (e_u, 1 - e_u) on both axes (no
+//   integer between u~ and the reference's correctly rounded quotient); then floor(u_ref) = f and the
+//   reference's "trunc toward zero into [0, W)" test is 0 <= f <= W - 1. Using |f| makes t fall outside
+//   [0, 1) for f < 0, so u in (-1, 0) - which the reference maps to column 0 (quirk q1) - is never
+//   decided here and is evaluated exactly.
 //   The depth test is decided when | |d - q~_z| - threshold | > E_z (+ fp32 rounding slack).
 // Anything non-finite, huge or degenerate fails a comparison and ends up in the exact queue.
-struct ViewConst {       // 20 floats = 80 B; 819 views fit the 64 KB constant bank
-  float P[12];           // fp32 image of K * inverse pose (rows 1,2 negated)
-  float ax, ay;          // 1.02 * E_x, 1.02 * E_y
-  float ez_rho;          // 1.02 * 1.03 * E_z
-  float zmin;            // 1024 * E_z; +inf disables the filter for this view (non-pinhole K, overflow)
-  float thr_lo, thr_hi;  // threshold -/+ E_z with directed rounding
-  float pad0, pad1;
+//
+// Arithmetic is packed two-wide where both axes share an operation (fma.rn.f32x2 etc. on sm_100a: the
+// x and y image rows of P, the floor trick, the border tests), the point coordinates are kept
+// duplicated in register pairs for that, and the camera table is laid out so that one 64-bit constant
+// load yields the (x-row, y-row) operand pair.
+struct ViewConst {        // 20 floats = 80 B; 819 views fit the 64 KB constant bank
+  float2 Pxy[4];          // (P_0j, P_1j): x and y image rows of K * inverse pose (rows 1,2 negated), fp32
+  float Pz[4];            // z row
+  float2 nA;              // (-A_u, -A_v)
+  float zmin;             // +inf disables the filter for this view (non-pinhole K, overflow)
+  float thr_lo, thr_hi;   // threshold -/+ E_z with directed rounding
+  float pad0, pad1, pad2;
 };
 static_assert(sizeof(ViewConst) == 80, "ViewConst layout");
 constexpr int kConstViews = 65536 / (int)sizeof(ViewConst);  // 819
@@ -217,21 +229,27 @@ constexpr int kTile = kThreads * kPts;         // points per CTA
 constexpr int kQueue = 256;                    // exact-path queue entries per warp
 constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23: x + kMagic (round down) = floor(x) + kMagic for |x| < 2^22
 
+__host__ __device__ inline double near_limit(int limit) { return 0.5 * (limit - 1) + 2.0 + 0.0014 * limit; }   // NL
+__host__ __device__ inline double coord_bound(int limit) { return 0.5 * (limit - 1) + near_limit(limit) + 1.0; }  // U
+
 // one thread per (scene, view slot): fp64 set-up of the filter constants
 __global__ void camera_prep_kernel(const float* __restrict__ inv_poses, const double* __restrict__ intrinsics,
                                    const int64_t* __restrict__ view_off, const float* __restrict__ bbox, int n_scenes,
-                                   int max_views, double threshold, ViewConst* __restrict__ out) {
+                                   int max_views, int height, int width, double threshold, ViewConst* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_scenes * max_views) return;
   const int scene = i / max_views, v = i - scene * max_views;
   ViewConst c;
 #pragma unroll
-  for (int j = 0; j < 12; ++j) c.P[j] = 0.f;
-  c.ax = c.ay = c.ez_rho = 0.f;
+  for (int j = 0; j < 4; ++j) {
+    c.Pxy[j] = make_float2(0.f, 0.f);
+    c.Pz[j] = 0.f;
+  }
+  c.nA = make_float2(0.f, 0.f);
   c.zmin = INFINITY;
   c.thr_lo = -INFINITY;
   c.thr_hi = INFINITY;
-  c.pad0 = c.pad1 = 0.f;
+  c.pad0 = c.pad1 = c.pad2 = 0.f;
   const int64_t v0 = view_off[scene];
   const int n_views = (int)(view_off[scene + 1] - v0);
   if (v < n_views) {
@@ -273,11 +291,13 @@ __global__ void camera_prep_kernel(const float* __restrict__ inv_poses, const do
     }
     if (ok) {
 #pragma unroll
-      for (int j = 0; j < 12; ++j) c.P[j] = (float)P[j];
-      c.ax = __double2float_ru(1.02 * E[0]);
-      c.ay = __double2float_ru(1.02 * E[1]);
-      c.ez_rho = __double2float_ru(1.02 * 1.03 * E[2]);
-      c.zmin = __double2float_ru(1024.0 * E[2]);
+      for (int j = 0; j < 4; ++j) {
+        c.Pxy[j] = make_float2((float)P[j], (float)P[4 + j]);
+        c.Pz[j] = (float)P[8 + j];
+      }
+      c.nA = make_float2(-__double2float_ru(1.02 * (E[0] + 1.03 * coord_bound(width) * E[2])),
+                         -__double2float_ru(1.02 * (E[1] + 1.03 * coord_bound(height) * E[2])));
+      c.zmin = __double2float_ru(fmax(1024.0 * E[2], fmax(4.0 * E[0], 4.0 * E[1])));
       const double lo = threshold - E[2], hi = threshold + E[2];
       c.thr_lo = __double2float_rd(lo - 4.0 * eps * fabs(lo) - 1e-30);   // NaN threshold: every comparison fails
       c.thr_hi = __double2float_ru(hi + 4.0 * eps * fabs(hi) + 1e-30);
@@ -297,8 +317,11 @@ struct FastParams {
   int64_t total_points;
   int scene0, max_views;
   int height, width;
-  float wf, cu, hu, cv, hv;  // width; centre and half-width of the admissible floor range [-1, limit - 1] per axis
-  float wm1, hm1;            // width - 1, height - 1
+  float wf;                 // width
+  unsigned idx_max;         // height * width - 1
+  float2 centre;            // ((W - 1) / 2, (H - 1) / 2): |floor - centre| <= centre  <=>  0 <= floor <= limit - 1
+  float2 near;              // NL per axis
+  float2 h0;                // 0.499999 - B per axis
   double threshold;
   uint32_t* records;  // [n_words][total_points], indexed by sorted position
   uint8_t* any_visible;
@@ -341,42 +364,48 @@ static __device__ __noinline__ void drain_queue(const uint32_t* __restrict__ que
 // the arithmetic of the next views instead of by occupancy. (Plain loads cannot do this: ptxas puts
 // every LDG of the loop on one scoreboard, so a consumer of the oldest gather also waits for the
 // newest - measured as 18-28 % of all stall samples on that one instruction.)
-__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
-               "l"(__cvta_generic_to_global(gmem_src))
-               : "memory");
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_base, unsigned index) {
+  asm volatile(
+      "{\n\t.reg .u64 a;\n\t"
+      "mad.wide.u32 a, %2, 4, %1;\n\t"
+      "cp.async.ca.shared.global [%0], [a], 4;\n\t}"
+      ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(__cvta_generic_to_global(gmem_base)), "r"(index)
+      : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void stage_project(const ViewConst& c, const FastParams& p, const float* __restrict__ depth,
-                                              const float (&x)[kPts], const float (&y)[kPts], const float (&z)[kPts],
+                                              const float2 (&x)[kPts], const float2 (&y)[kPts], const float2 (&z)[kPts],
                                               float (&qz_out)[kPts], float* __restrict__ s_slot) {
   asm volatile("" : "+l"(depth));  // keep the view's base pointer in a register pair (one IMAD.WIDE per gather)
+  const float2 magic = make_float2(kMagic, kMagic), neg_magic = make_float2(-kMagic, -kMagic);
+  const float2 neg_half = make_float2(-0.5f, -0.5f), neg_centre = make_float2(-p.centre.x, -p.centre.y);
 #pragma unroll
   for (int k = 0; k < kPts; ++k) {
-    const float qx = fmaf(c.P[0], x[k], fmaf(c.P[1], y[k], fmaf(c.P[2], z[k], c.P[3])));
-    const float qy = fmaf(c.P[4], x[k], fmaf(c.P[5], y[k], fmaf(c.P[6], z[k], c.P[7])));
-    const float qz = fmaf(c.P[8], x[k], fmaf(c.P[9], y[k], fmaf(c.P[10], z[k], c.P[11])));
+    // (x, y image rows) two-wide; x[k] = (x, x) etc.
+    const float2 qxy = __ffma2_rn(c.Pxy[0], x[k], __ffma2_rn(c.Pxy[1], y[k], __ffma2_rn(c.Pxy[2], z[k], c.Pxy[3])));
+    const float qz = fmaf(c.Pz[0], x[k].x, fmaf(c.Pz[1], y[k].x, fmaf(c.Pz[2], z[k].x, c.Pz[3])));
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(qz));
-    const float ar = fabsf(r);
-    const float u = qx * r, w = qy * r;
-    const float rho = fmaf(c.ez_rho, ar, 3.04e-07f);                     // 1.02 * (1.03 E_z |r| + 5 eps)
-    const float h_u = fmaf(-fabsf(u), rho, fmaf(-c.ax, ar, 0.499999f));  // 0.5 - e_u - slack for the fp32 evaluation of e_u
-    const float h_v = fmaf(-fabsf(w), rho, fmaf(-c.ay, ar, 0.499999f));
-    const float fu = __fadd_rd(u, kMagic) - kMagic;  // floor(u) while |u| < 2^22 (guaranteed when h_u > 0)
-    const float fv = __fadd_rd(w, kMagic) - kMagic;
-    const float gu = (u - fu) - 0.5f, gv = (w - fv) - 0.5f;
-    const bool decided = (fabsf(qz) >= c.zmin) && (fabsf(gu) < h_u) && (fabsf(gv) < h_v);
-    const bool inside = (fabsf(fu - p.cu) <= p.hu) && (fabsf(fv - p.cv) <= p.hv);  // -1 <= floor <= limit - 1
-    // The gather is issued unconditionally at the pixel clamped into the image (no predicate has to
-    // outlive the arithmetic; NaN clamps to 0). integer-valued float < 2^23 -> index without a
-    // conversion instruction: the low mantissa bits of pix + 2^23 are the index.
-    const float fuc = fminf(fmaxf(fu, 0.f), p.wm1), fvc = fminf(fmaxf(fv, 0.f), p.hm1);
-    const unsigned pix = (unsigned)__float_as_int(fmaf(fvc, p.wf, fuc) + 8388608.0f) & 0x7fffffu;
-    cp_async_f32(s_slot + k * kThreads, depth + pix);
+    const float2 rr = make_float2(r, r);
+    const float2 uw = __fmul2_rn(qxy, rr);                       // (u~, v~)
+    const float2 h = __ffma2_rn(c.nA, rr, p.h0);                 // 0.5 - e per axis (r > 0 whenever the pair is sane)
+    const float2 f = __fadd2_rn(__fadd2_rd(uw, magic), neg_magic);  // floor, exact while |u~| < 2^22
+    const float tu = uw.x - fabsf(f.x), tv = uw.y - fabsf(f.y);     // fractional part; outside [0, 1) when floor < 0
+    const float2 g = __fadd2_rn(make_float2(tu, tv), neg_half);
+    const float2 a = __fadd2_rn(f, neg_centre);
+    const bool not_near = (fabsf(a.x) > p.near.x) || (fabsf(a.y) > p.near.y);
+    const bool frac_ok = (fabsf(g.x) < h.x) && (fabsf(g.y) < h.y);
+    const bool decided = (qz >= c.zmin) && (not_near || frac_ok);
+    const bool inside = (fabsf(a.x) <= p.centre.x) && (fabsf(a.y) <= p.centre.y);
+    // The gather is issued unconditionally (no predicate has to outlive the arithmetic) at a pixel index
+    // forced into the image: for a pair inside the image fv * W + fu is an integer-valued float < 2^23
+    // whose index is the low mantissa bits of idx + 2^23 (no conversion instruction); anything else
+    // (negative, NaN, huge) yields arbitrary bits that the unsigned min clamps to a valid pixel.
+    const unsigned pix = min((unsigned)__float_as_int(fmaf(f.y, p.wf, f.x) + 8388608.0f) & 0x7fffffu, p.idx_max);
+    cp_async_f32(s_slot + k * kThreads, depth, pix);
     // No flag travels with the gather either. A pixel decided to be outside the image records
     // z = +inf: |depth - inf| fails "<= thr_lo" and passes "> thr_hi" (decided, not visible). An
     // undecided pixel records z = NaN, which fails both tests (-> exact queue), exactly like a NaN
@@ -405,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 2) visibility_filter_kernel(const __
   // Slots past the end of the scene re-evaluate its last point (results are never written out), so
   // the loop carries no per-point validity test. Points that must not enter the filter (non-finite
   // or huge coordinates) carry NaN, which fails every comparison and lands in the exact queue.
-  float x[kPts], y[kPts], z[kPts];
+  float2 x[kPts], y[kPts], z[kPts];  // each coordinate duplicated: operands of the two-wide instructions
   uint32_t word[kPts];
 #pragma unroll
   for (int k = 0; k < kPts; ++k) {
@@ -414,9 +443,10 @@ __global__ void __launch_bounds__(kThreads, 2) visibility_filter_kernel(const __
     const float fx = (float)__ldg(p.points + 3 * orig), fy = (float)__ldg(p.points + 3 * orig + 1),
                 fz = (float)__ldg(p.points + 3 * orig + 2);
     const bool tame = fabsf(fx) < kHuge && fabsf(fy) < kHuge && fabsf(fz) < kHuge;  // NaN -> false; same rule as the bbox pass
-    x[k] = tame ? fx : __int_as_float(0x7fc00000);
-    y[k] = fy;
-    z[k] = fz;
+    const float fx_or_nan = tame ? fx : __int_as_float(0x7fc00000);
+    x[k] = make_float2(fx_or_nan, fx_or_nan);
+    y[k] = make_float2(fy, fy);
+    z[k] = make_float2(fz, fz);
     word[k] = 0;
     for (int w = 0; w < n_words; ++w) s_rec[w * kTile + local] = 0;
     for (int g = 0; g < 3; ++g) s_sensor[g * kTile + k * kThreads] = 0.f;  // slots never hold junk NaN/inf patterns
@@ -598,7 +628,7 @@ int dc_project_visibility_sorted(const double* points, const int64_t* point_off,
   cell_scatter_kernel<<<g1, kThreads, 0, st>>>(points, point_off, w.bbox, w.counts, w.perm, rank);
   ViewConst* vc = reinterpret_cast<ViewConst*>(w.view_consts);
   camera_prep_kernel<<<dc::ceil_div(n_scenes * max_views_per_scene, 128), 128, 0, st>>>(
-      inv_poses, intrinsics, view_off, w.bbox, n_scenes, max_views_per_scene, threshold, vc);
+      inv_poses, intrinsics, view_off, w.bbox, n_scenes, max_views_per_scene, height, width, threshold, vc);
   DC_LAUNCH_CHECK();
   if (smem > 48 * 1024)
     DC_CUDA(cudaFuncSetAttribute(visibility_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -612,9 +642,12 @@ int dc_project_visibility_sorted(const double* points, const int64_t* point_off,
     DC_CUDA(cudaMemcpyToSymbolAsync(c_views, vc + (size_t)s0 * max_views_per_scene,
                                     sizeof(ViewConst) * (size_t)ns * max_views_per_scene, 0, cudaMemcpyDeviceToDevice, st));
     FastParams p{points, point_off, view_off, depths, inv_poses, intrinsics, w.perm, total_points, s0,
-                 max_views_per_scene, height, width, (float)width, 0.5f * (float)(width - 2), 0.5f * (float)width,
-                 0.5f * (float)(height - 2), 0.5f * (float)height, (float)(width - 1), (float)(height - 1), threshold, records,
-                 any_visible};
+                 max_views_per_scene, height, width, (float)width, (unsigned)((int64_t)height * width - 1),
+                 make_float2(0.5f * (float)(width - 1), 0.5f * (float)(height - 1)),
+                 make_float2((float)near_limit(width), (float)near_limit(height)),
+                 make_float2((float)(0.499999 - 1.02 * 5.0 * 5.9604644775390625e-08 * coord_bound(width)),
+                             (float)(0.499999 - 1.02 * 5.0 * 5.9604644775390625e-08 * coord_bound(height))),
+                 threshold, records, any_visible};
     dim3 grid((unsigned)ctas_per_scene, (unsigned)ns);
     visibility_filter_kernel<<<grid, kThreads, smem, st>>>(p);
   }
