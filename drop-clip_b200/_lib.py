@@ -59,6 +59,9 @@ SIGNATURES = {
     "dc_unique_max_pool": (c_int, [P, P, c_int, c_int, c_int64, P, P, P, P, c_size_t, P]),
     "dc_voxel_down_mean": (c_int, [P, c_int64, c_double, P, P, P, P, c_size_t, P]),
     "dc_nearest_index": (c_int, [P, c_int64, P, c_int64, P, P, P]),
+    "dc_binary_iou_counts": (c_int, [P, P, c_int, P, c_int, c_int64, c_float, c_int, c_int, P, P, P]),
+    "dc_class_iou_workspace": (c_size_t, [c_int]),
+    "dc_class_iou_hist": (c_int, [P, P, c_int, c_int64, c_int, c_int64, P, P, P, P, c_size_t, P]),
     "dc_host_gather_copy": (c_int, [P, c_int64, c_int64, P, c_int]),
     "dc_host_gather_narrow_i64_u8": (c_int, [P, c_int64, c_int64, P, c_int, POINTER(c_int)]),
 }

@@ -318,6 +318,24 @@ DC_API int dc_voxel_down_mean(const double* points, int64_t n, double voxel_size
 DC_API int dc_nearest_index(const double* query, int64_t m, const double* ref, int64_t n, int64_t* out_index,
                      double* out_dist2, dc_stream_t stream);
 
+/* ---- metric counts that follow the grounding kernel ----
+ * dc_binary_iou_counts: trainMetricPC utils/misc.py:21-50 for a ragged batch of instances
+ * (inst_off[n_instances + 1]): pred is binarised at `threshold` exactly like `pred[pred < thr] = 0;
+ * pred[pred >= thr] = 1` (NaN stays NaN and counts as set), written back in place when
+ * binarize_in_place != 0 and no sigmoid is applied (the reference mutates the caller's tensor then);
+ * inter / uni [n_instances] int64 = |pred & gt|, |pred | gt|. gt dtype: DC_U8 (bool), DC_I32, DC_I64, DC_F32.
+ * dc_class_iou_hist: intersectionAndUnionGPU utils/misc.py:186-199 - output[target == ignore_index] =
+ * ignore_index in place, then the K-bin histograms of output[output == target], output and target
+ * (torch.histc(bins=K, min=0, max=K-1) maps class c in [0, K-1] to bin c); fp32 results,
+ * area_union = area_output + area_target - area_intersection. */
+DC_API int dc_binary_iou_counts(float* pred, const void* gt, int gt_dtype, const int64_t* inst_off, int n_instances,
+                         int64_t max_points_per_instance, float threshold, int apply_sigmoid, int binarize_in_place,
+                         int64_t* inter, int64_t* uni, dc_stream_t stream);
+DC_API size_t dc_class_iou_workspace(int n_classes);
+DC_API int dc_class_iou_hist(void* output, const void* target, int dtype, int64_t n, int n_classes, int64_t ignore_index,
+                      float* area_intersection, float* area_union, float* area_target, void* workspace,
+                      size_t workspace_bytes, dc_stream_t stream);
+
 /* ---- host-side staging (no device work): used by the Python drop-in to fill pinned upload buffers ----
  * dc_host_gather_copy: dst[i * item_bytes ...] = srcs[i][0 .. item_bytes) for n_items host arrays, on n_threads
  * threads. dc_host_gather_narrow_i64_u8: same for int64 arrays of item_elems elements narrowed to uint8;
