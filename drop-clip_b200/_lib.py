@@ -58,6 +58,7 @@ SIGNATURES = {
     "dc_sort_workspace": (c_size_t, [c_int64]),
     "dc_unique_max_pool": (c_int, [P, P, c_int, c_int, c_int64, P, P, P, P, c_size_t, P]),
     "dc_voxel_down_mean": (c_int, [P, c_int64, c_double, P, P, P, P, c_size_t, P]),
+    "dc_voxel_down_trace": (c_int, [P, P, P, c_int64, c_double, P, P, P, P, P, P, P, c_size_t, P]),
     "dc_nearest_index": (c_int, [P, c_int64, P, c_int64, P, P, P]),
     "dc_binary_iou_counts": (c_int, [P, P, c_int, P, c_int, c_int64, c_float, c_int, c_int, P, P, P]),
     "dc_class_iou_workspace": (c_size_t, [c_int]),

@@ -49,6 +49,77 @@ def voxel_down(points, voxel_size: float, return_first_index: bool = False):
     return (out[:m], first[:m]) if return_first_index else out[:m]
 
 
+def voxel_down_trace(points, colors, labels, voxel_size: float):
+    """Open3D `voxel_down_sample_and_trace` followed by the label majority vote of
+    aggregate_views_blender_new (utils/geometry.py:186-201), on the device: returns CUDA tensors
+    (points (M,3) f64, colors (M,3) f64, labels (M,) i64, counts (M,) i64), voxels ordered by voxel index."""
+    lib = _lib.load()
+    pts = _f64(points)
+    n = pts.shape[0]
+    dev = pts.device
+    cols = _f64(colors) if colors is not None else None
+    labs = None
+    if labels is not None:
+        labs = (labels if isinstance(labels, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(labels))).to(dev, torch.int64)
+        labs = labs.reshape(-1).contiguous()
+    out_p = torch.empty((max(n, 1), 3), dtype=torch.float64, device=dev)
+    out_c = torch.empty((max(n, 1), 3), dtype=torch.float64, device=dev) if cols is not None else None
+    out_l = torch.empty(max(n, 1), dtype=torch.int64, device=dev) if labs is not None else None
+    counts = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    m_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = _workspace(n)
+    check(lib.dc_voxel_down_trace(ptr(pts), ptr(cols), ptr(labs), n, float(voxel_size), ptr(out_p), ptr(out_c), ptr(out_l),
+                                  None, ptr(counts), ptr(m_dev), ptr(ws), ws.numel(), current_stream()))
+    m = int(m_dev.item())
+    return out_p[:m], (out_c[:m] if out_c is not None else None), (out_l[:m] if out_l is not None else None), counts[:m]
+
+
+def binary_masks_to_seg(masks, obj_ids=None):
+    """utils/image.py:11-15 (host numpy; defines the instance-map dtype the hot path receives)."""
+    if obj_ids is None:
+        obj_ids = np.arange(masks.shape[0], dtype=np.uint8)
+    return np.max(masks * obj_ids[:, None, None], axis=0)
+
+
+def aggregate_views_blender_new(scene, camera_intrinsic, depth_trunc=25.0, voxel_size=None):
+    """utils/geometry.py:120-204: back-project every view's valid pixels (depth < depth_trunc), flip to the
+    Blender camera convention, move to the world frame, concatenate, and - with `voxel_size` - voxel-grid
+    down-sample with mean position / colour and majority-vote instance label. Same arguments and return
+    triple (numpy points, colors, labels) as the reference; all arithmetic on the device. Voxels come out
+    ordered by voxel index (Open3D's order is its hash map's iteration order)."""
+    dev = _dev()
+    from .projections import backproject
+    col_to_ins = scene["col_to_ins"]
+    all_p, all_c, all_l = [], [], []
+    for _, stuff in scene["views"].items():
+        rgb = stuff["rgb"]
+        depth = np.ascontiguousarray(stuff["depth"], dtype=np.float32)
+        _, binary_masks, colors = zip(*stuff["annos"])
+        seg = binary_masks_to_seg(np.stack(binary_masks), np.asarray([col_to_ins[x] for x in colors]))
+        d = torch.from_numpy(depth).to(dev)
+        valid_m = (d < float(depth_trunc)).reshape(-1)  # seg_ins_2d[valid_m]
+        d0 = torch.where(d >= float(depth_trunc), torch.zeros_like(d), d)
+        keep = (d0 > 0).reshape(-1)                     # Open3D keeps 0 < depth < trunc
+        pts = backproject(d0, camera_intrinsic, o3d_rounding=True)[0].reshape(-1, 3)[keep]
+        pts = (pts * torch.tensor([1.0, -1.0, -1.0], dtype=torch.float64, device=dev)).contiguous()  # pc.transform(T_cam)
+        # camera -> world with the view's fp32 world_matrix promoted to fp64 (utils/geometry.py:163-164)
+        world = np.ascontiguousarray(np.asarray(stuff["camera"]["world_matrix"]), dtype=np.float32).reshape(16)
+        out = torch.empty_like(pts)
+        check(_lib.load().dc_transform_points(ptr(pts), pts.shape[0], world.ctypes.data_as(_lib.c_void_p), ptr(out),
+                                              current_stream()))
+        pts = out
+        all_p.append(pts)
+        all_c.append(torch.from_numpy(np.ascontiguousarray(rgb)).to(dev).reshape(-1, rgb.shape[-1])[keep].to(torch.float64))
+        all_l.append(torch.from_numpy(np.ascontiguousarray(seg)).to(dev).reshape(-1)[valid_m].to(torch.int64))
+    pts, cols, labs = torch.cat(all_p), torch.cat(all_c), torch.cat(all_l)
+    if voxel_size is None:
+        return pts.cpu().numpy(), cols.cpu().numpy() / 255.0, labs.cpu().numpy()
+    # colours are divided by 255 before the down-sampling in Open3D (the cloud stores [0, 1] colours)
+    cols = torch.from_numpy(cols.cpu().numpy() / 255.0).to(dev)
+    p, c, l, _ = voxel_down_trace(pts, cols, labs, voxel_size)
+    return p.cpu().numpy(), c.cpu().numpy(), l.cpu().numpy()
+
+
 def pc_voxel_down(pc, voxel_size=0.0075):
     return voxel_down(pc, voxel_size).cpu().numpy()
 

@@ -313,6 +313,14 @@ DC_API int dc_unique_max_pool(const double* points, const void* feats, int feat_
 DC_API int dc_voxel_down_mean(const double* points, int64_t n, double voxel_size, double* out_points,
                        int64_t* first_index, int64_t* n_voxels, void* workspace, size_t workspace_bytes,
                        dc_stream_t stream);
+/* voxel_down_sample_and_trace + label majority vote of aggregate_views_blender_new utils/geometry.py:186-201
+ * (Open3D semantics, parity unpinned): per voxel the mean position, the mean colour (optional) and the most
+ * frequent label (optional; ties: the label met first in point order, like Counter.most_common()[0][0]);
+ * counts[u] = members of voxel u. Voxels ordered by voxel index. workspace: dc_sort_workspace(n). */
+DC_API int dc_voxel_down_trace(const double* points, const double* colors, const int64_t* labels, int64_t n,
+                        double voxel_size, double* out_points, double* out_colors, int64_t* out_labels,
+                        int64_t* first_index, int64_t* counts, int64_t* n_voxels, void* workspace,
+                        size_t workspace_bytes, dc_stream_t stream);
 /* find_closest_indices utils/geometry.py:390-401 (cKDTree.query k=1): exact fp64 nearest neighbour
  * of every query point in `ref` (ties: smallest index); out_dist2 (squared distance) may be NULL. */
 DC_API int dc_nearest_index(const double* query, int64_t m, const double* ref, int64_t n, int64_t* out_index,

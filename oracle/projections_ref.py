@@ -181,3 +181,60 @@ def rgbd_points_ref(rgb, depth, intr, depth_scale=1.0, depth_trunc=25.0):
     x = (u - intr["cx"]) * z / intr["fx"]
     y = (v - intr["cy"]) * z / intr["fy"]
     return np.stack([x, y, z], axis=1), rgb[v, u].astype(np.float64) / 255.0
+
+
+# ------------------------------------------------------------------------------------------------
+# Aggregation step upstream of the fusion path: aggregate_views_blender_new
+# utils/geometry.py:120-204. PARITY UNPINNED (Open3D create_from_rgbd_image / transform /
+# voxel_down_sample_and_trace are restated from their published semantics; no fixture exists).
+def voxel_down_trace_ref(points, colors, labels, voxel_size):
+    """Per voxel: mean point, mean colour, Counter(labels).most_common()[0][0], member count; voxel order = key order."""
+    from collections import Counter
+    pts = np.asarray(points, dtype=np.float64)
+    origin = pts.min(axis=0) - voxel_size * 0.5
+    idx = np.floor((pts - origin) / voxel_size).astype(np.int64)
+    key = (idx[:, 0] << 42) | (idx[:, 1] << 21) | idx[:, 2]
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]])
+    ends = np.r_[starts[1:], len(ks)]
+    out_p = np.empty((len(starts), 3))
+    out_c = np.empty((len(starts), 3))
+    out_l = np.empty(len(starts), dtype=np.int64)
+    cnt = np.empty(len(starts), dtype=np.int64)
+    for u, (a, b) in enumerate(zip(starts, ends)):
+        sp, sc = np.zeros(3), np.zeros(3)
+        for j in order[a:b]:
+            sp = sp + pts[j]
+            sc = sc + colors[j]
+        out_p[u], out_c[u] = sp / float(b - a), sc / float(b - a)
+        out_l[u] = Counter(labels[order[a:b]].tolist()).most_common()[0][0]  # utils/geometry.py:197
+        cnt[u] = b - a
+    return out_p, out_c, out_l, cnt
+
+
+def binary_masks_to_seg_ref(masks, obj_ids):
+    """utils/image.py:11-15."""
+    return np.max(masks * obj_ids[:, None, None], axis=0)
+
+
+def aggregate_views_ref(scene, intr, depth_trunc=25.0, voxel_size=None):
+    """utils/geometry.py:120-204 with the Open3D calls restated."""
+    pts, cols, labs = [], [], []
+    for _, stuff in scene["views"].items():
+        rgb, depth = stuff["rgb"], stuff["depth"].astype(np.float32)
+        valid = depth < depth_trunc
+        _, masks, colors = zip(*stuff["annos"])
+        seg = binary_masks_to_seg_ref(np.stack(masks), np.asarray([scene["col_to_ins"][c] for c in colors]))
+        labs.append(seg[valid].flatten())
+        p, c = rgbd_points_ref(rgb, depth, intr, depth_trunc=depth_trunc)
+        p = p * np.array([1.0, -1.0, -1.0])  # T_cam
+        m = np.asarray(stuff["camera"]["world_matrix"]).astype(np.float64)
+        p = p @ m[:3, :3].T + m[:3, 3]
+        pts.append(p)
+        cols.append(c)
+    pts, cols, labs = np.concatenate(pts), np.concatenate(cols), np.concatenate(labs)
+    if voxel_size is None:
+        return pts, cols, labs
+    p, c, l, _ = voxel_down_trace_ref(pts, cols, labs, voxel_size)
+    return p, c, l

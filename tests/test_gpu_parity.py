@@ -648,3 +648,55 @@ def test_sorted_visibility_full_size_scene_vs_direct():
     assert torch.equal(eng.unpack_visibility(b, records, rank, torch.uint8), direct)
     assert torch.equal(any_s, any_d)
     assert 0.2 < direct.float().mean().item() < 0.9
+
+
+# ---------------------------------------------------------------------------------------------- §8f-1 aggregation step
+def _aggregation_scene(seed=21, n_views=3, h=60, w=80):
+    """A scene dict in the layout data/blender.py hands to aggregate_views_blender_new."""
+    from dropclip_b200.scenes import small_scene
+    sc = small_scene(seed, n_views=n_views, n_points=200, n_objects=5, height=h, width=w)
+    rng = np.random.default_rng(seed)
+    ids = sorted(int(i) for i in np.unique(np.stack(sc.seg_masks)))
+    col_to_ins = {(i, i, i): i for i in ids}
+    views = {}
+    for v in range(n_views):
+        seg = sc.seg_masks[v]
+        annos = [(f"obj{i}", seg == i, (i, i, i)) for i in ids if (seg == i).any()]
+        views[v] = {"rgb": rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8), "depth": sc.depths[v], "annos": annos,
+                    "camera": {"world_matrix": sc.camera_poses[v]}}
+    return {"col_to_ins": col_to_ins, "views": views}, sc.intrinsic
+
+
+def test_voxel_down_trace_vs_restatement():
+    from oracle import projections_ref as pr
+    from dropclip_b200 import geometry as geo
+    rng = np.random.default_rng(4)
+    pts = rng.uniform(-1, 1, size=(30000, 3))
+    cols = rng.random((30000, 3))
+    labs = rng.integers(0, 4, size=30000)
+    labs[::3] = 77  # a dominant label, plus many ties at coarse resolution
+    for vs in (0.05, 0.3, 5.0):  # 5.0: a single voxel with > 8 distinct labels is impossible here; see below
+        p, c, l, n = geo.voxel_down_trace(pts, cols, labs, vs)
+        wp, wc, wl, wn = pr.voxel_down_trace_ref(pts, cols, labs, vs)
+        assert np.array_equal(n.cpu().numpy(), wn) and np.array_equal(l.cpu().numpy(), wl)
+        assert np.array_equal(p.cpu().numpy(), wp) and np.array_equal(c.cpu().numpy(), wc)
+    many = rng.integers(0, 40, size=30000)  # > 8 distinct labels per voxel -> quadratic fallback
+    _, _, l, _ = geo.voxel_down_trace(pts, cols, many, 0.5)
+    assert np.array_equal(l.cpu().numpy(), pr.voxel_down_trace_ref(pts, cols, many, 0.5)[2])
+
+
+def test_aggregate_views_blender_new_vs_restatement():
+    """utils/geometry.py:120-204 (parity unpinned: Open3D semantics restated in oracle/projections_ref.py)."""
+    from oracle import projections_ref as pr
+    from dropclip_b200 import geometry as geo
+    scene, intr = _aggregation_scene()
+    p, c, l = geo.aggregate_views_blender_new(scene, intr, depth_trunc=25.0, voxel_size=None)
+    wp, wc, wl = pr.aggregate_views_ref(scene, intr, 25.0, None)
+    assert p.shape == wp.shape and np.array_equal(l, wl) and np.array_equal(c, wc)
+    assert np.allclose(p, wp, rtol=0, atol=1e-12)
+    for vs in (0.2, 1.0):
+        p, c, l = geo.aggregate_views_blender_new(scene, intr, depth_trunc=25.0, voxel_size=vs)
+        wp, wc, wl = pr.aggregate_views_ref(scene, intr, 25.0, vs)
+        assert p.shape == wp.shape and p.shape[0] < 3 * 60 * 80
+        assert np.array_equal(l, wl)
+        assert np.allclose(p, wp, rtol=0, atol=1e-11) and np.allclose(c, wc, rtol=0, atol=1e-12)
