@@ -63,6 +63,9 @@ SIGNATURES = {
     "dc_binary_iou_counts": (c_int, [P, P, c_int, P, c_int, c_int64, c_float, c_int, c_int, P, P, P]),
     "dc_class_iou_workspace": (c_size_t, [c_int]),
     "dc_class_iou_hist": (c_int, [P, P, c_int, c_int64, c_int, c_int64, P, P, P, P, c_size_t, P]),
+    "dc_sample_keep_flags": (c_int, [P, P, P, P, P, c_int, c_int64, P, P]),
+    "dc_sample_gather": (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int, c_int64, c_int64, c_int64, c_int, c_int, P, P, P, P,
+                                 P, P, P, P, P]),
     "dc_host_gather_copy": (c_int, [P, c_int64, c_int64, P, c_int]),
     "dc_host_gather_narrow_i64_u8": (c_int, [P, c_int64, c_int64, P, c_int, POINTER(c_int)]),
 }

@@ -344,6 +344,26 @@ DC_API int dc_class_iou_hist(void* output, const void* target, int dtype, int64_
                       float* area_intersection, float* area_union, float* area_target, void* workspace,
                       size_t workspace_bytes, dc_stream_t stream);
 
+/* ---- training-sample assembly: MVDistilDataset.__getitem__ data/dataset_blender.py:330-362,400-414
+ * for a ragged batch of samples; random choices (views, point indices) are inputs.
+ * dc_sample_keep_flags: keep[j] = OR over the sample's view_list of vis_mask[v, j] (vis_mask: per sample a (V_s, N_s)
+ *   uint8 block at mask_off[s]); an empty view list keeps every point (use_full_pc).
+ * dc_sample_gather: with new_index / kept_off from dc_compact_scan(keep): row r of sample s = kept point number
+ *   indices[r]; out_xyz = float(xyz - column mean of the selected rows) (numpy's sequential axis-0 mean, fp64),
+ *   out_rgb = float(rgb), out_label = label (through uint8 when label_as_u8, like `.astype(np.uint8)` at :349),
+ *   out_feat[r] = per_obj[obj_off[s] + label]  (feat[label], :128-130). Scratch: rows / kept_idx int64
+ *   [total_rows] / [total_points], mean [3 * n_samples] fp64. *error: 1 = index out of range, 2 = label without
+ *   a per_obj row (numpy raises IndexError in both cases). */
+DC_API int dc_sample_keep_flags(const uint8_t* vis_mask, const int64_t* mask_off, const int64_t* point_off,
+                         const int32_t* view_list, const int64_t* view_list_off, int n_samples,
+                         int64_t max_points_per_sample, uint8_t* keep, dc_stream_t stream);
+DC_API int dc_sample_gather(const double* xyz, const double* rgb, const int64_t* label, const float* per_obj,
+                     const int64_t* obj_off, const uint8_t* keep, const int64_t* new_index, const int64_t* kept_off,
+                     const int64_t* point_off, const int64_t* indices, const int64_t* out_off, int n_samples,
+                     int64_t total_points, int64_t total_rows, int64_t max_rows_per_sample, int dim, int label_as_u8,
+                     float* out_xyz, float* out_rgb, int32_t* out_label, float* out_feat, int64_t* rows,
+                     int64_t* kept_idx, double* mean, int* error, dc_stream_t stream);
+
 /* ---- host-side staging (no device work): used by the Python drop-in to fill pinned upload buffers ----
  * dc_host_gather_copy: dst[i * item_bytes ...] = srcs[i][0 .. item_bytes) for n_items host arrays, on n_threads
  * threads. dc_host_gather_narrow_i64_u8: same for int64 arrays of item_elems elements narrowed to uint8;
