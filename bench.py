@@ -190,7 +190,8 @@ def run_ours(args):
 
     def step():
         res = eng.fuse_object_level(batch, 0.05, False, True, "max", torch.uint8)
-        comp = eng.compact_visibility(batch, res["any_visible"], res["records"], res["rank"], torch.uint8)
+        # device-resident consumer: sizes and block layout of the compacted masks stay on the GPU (no host sync)
+        comp = eng.compact_visibility(batch, res["any_visible"], res["records"], res["rank"], torch.uint8, host_sizes=False)
         if world > 1:
             gathered = torch.empty((world,) + tuple(res["fused"].shape), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(gathered, res["fused"])

@@ -40,6 +40,7 @@ SIGNATURES = {
     "dc_scatter_to_points": (c_int, [P, P, P, P, c_int, c_int64, c_int, c_int, P, P]),
     "dc_compact_workspace": (c_size_t, [c_int64]),
     "dc_compact_scan": (c_int, [P, c_int64, P, c_int, P, P, P, c_size_t, P]),
+    "dc_compact_mask_offsets": (c_int, [P, P, c_int, P, P]),
     "dc_compact_rows": (c_int, [P, c_int64, P, P, c_int64, P, P]),
     "dc_compact_mask": (c_int, [P, c_int, P, P, P, P, P, P, P, c_int, c_int64, c_int, P, P]),
     "dc_pixel_fuse": (c_int, [P, P, P, P, P, P, P, P, c_int, P, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int64,

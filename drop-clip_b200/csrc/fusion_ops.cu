@@ -200,6 +200,18 @@ __global__ void kept_offsets_kernel(const uint8_t* __restrict__ flags, const int
   kept_off[s] = (j < total) ? new_index[j] : (total > 0 ? new_index[total - 1] + (flags[total - 1] != 0) : 0);
 }
 
+// out_off[s] = sum over earlier scenes of views * kept points: the layout of the compacted (V_s, N'_s) blocks
+__global__ void mask_offsets_kernel(const int64_t* __restrict__ kept_off, const int64_t* __restrict__ view_off, int n_scenes,
+                                    int64_t* __restrict__ out_off) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int64_t run = 0;
+  for (int s = 0; s < n_scenes; ++s) {
+    out_off[s] = run;
+    run += (view_off[s + 1] - view_off[s]) * (kept_off[s + 1] - kept_off[s]);
+  }
+  out_off[n_scenes] = run;
+}
+
 // rows of row_bytes (multiple of 4): one thread per 4-byte word
 __global__ void __launch_bounds__(256) compact_rows_kernel(const uint32_t* __restrict__ in, int words_per_row,
                                                            const uint8_t* __restrict__ flags,
@@ -302,6 +314,13 @@ int dc_compact_scan(const uint8_t* any_visible, int64_t total_points, const int6
   scan_block_sums_kernel<<<1, 1024, 0, st>>>(block_sums, n_blocks);
   scan_rank_kernel<<<(unsigned)n_blocks, kScanThreads, 0, st>>>(any_visible, total_points, block_sums, new_index);
   kept_offsets_kernel<<<dc::ceil_div(n_scenes + 1, 128), 128, 0, st>>>(any_visible, new_index, point_off, n_scenes, total_points, kept_off);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+int dc_compact_mask_offsets(const int64_t* kept_off, const int64_t* view_off, int n_scenes, int64_t* out_off, dc_stream_t stream) {
+  DC_CHECK_ARG(kept_off && view_off && out_off && n_scenes >= 0, "dc_compact_mask_offsets: bad argument");
+  mask_offsets_kernel<<<1, 32, 0, dc::as_stream(stream)>>>(kept_off, view_off, n_scenes, out_off);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

@@ -408,9 +408,13 @@ class FusionEngine:
         return mask
 
     def compact_visibility(self, b: SceneBatch, any_vis, records, rank, out_dtype=torch.uint8,
-                           extra_rows: Sequence[torch.Tensor] = ()):
+                           extra_rows: Sequence[torch.Tensor] = (), host_sizes: bool = True):
         """Drops never-visible points and expands the bit records straight into the compacted masks.
-        Returns (new_index, kept_off, kept_host, out_off_host, compacted mask, compacted rows)."""
+        Returns (new_index, kept_off, kept_host, out_off_host, compacted mask, compacted rows).
+
+        With `host_sizes=False` nothing is read back: the outputs are allocated at their upper bound (the
+        uncompacted sizes), the block layout stays on the device (kept_off, and out_off returned in place of
+        out_off_host) and kept_host is None - the form a device-resident consumer uses (bench.py's step)."""
         n = b.total_points
         new_index = torch.empty(max(n, 1), dtype=torch.int64, device=b.device)
         kept_off = torch.empty(b.n_scenes + 1, dtype=torch.int64, device=b.device)
@@ -419,10 +423,18 @@ class FusionEngine:
         check(self.lib.dc_compact_scan(ptr(any_vis), n, ptr(b.off["point"]), b.n_scenes, ptr(new_index), ptr(kept_off),
                                        ptr(ws), ws_bytes, current_stream()))
         self.launches += 4
-        kept_host = kept_off.cpu().numpy()
-        out_off_host = _prefix([v * k for v, k in zip(b.n_views, np.diff(kept_host))])
-        out_off = torch.from_numpy(out_off_host).to(b.device)
-        cmask = torch.empty(int(out_off_host[-1]), dtype=out_dtype, device=b.device)
+        if host_sizes:
+            kept_host = kept_off.cpu().numpy()
+            out_off_host = _prefix([v * k for v, k in zip(b.n_views, np.diff(kept_host))])
+            out_off = torch.from_numpy(out_off_host).to(b.device)
+            mask_elems, n_kept = int(out_off_host[-1]), int(kept_host[-1])
+        else:
+            kept_host, out_off_host = None, None
+            out_off = torch.empty(b.n_scenes + 1, dtype=torch.int64, device=b.device)
+            check(self.lib.dc_compact_mask_offsets(ptr(kept_off), ptr(b.off["view"]), b.n_scenes, ptr(out_off), current_stream()))
+            self.launches += 1
+            mask_elems, n_kept = int(b.off_host["mask"][-1]), n
+        cmask = torch.empty(mask_elems, dtype=out_dtype, device=b.device)
         with self._tick("unpack_compact"):
             check(self.lib.dc_unpack_visibility_compact(ptr(records), ptr(rank), ptr(b.off["point"]), ptr(b.off["view"]),
                                                         ptr(any_vis), ptr(new_index), ptr(kept_off), ptr(out_off), b.n_scenes, n,
@@ -432,12 +444,12 @@ class FusionEngine:
         rows_out = []
         for t in extra_rows:
             t2 = t.reshape(n, -1)
-            o = torch.empty((int(kept_host[-1]), t2.shape[1]), dtype=t.dtype, device=b.device)
+            o = torch.empty((n_kept, t2.shape[1]), dtype=t.dtype, device=b.device)
             check(self.lib.dc_compact_rows(ptr(t2), t2.shape[1] * t2.element_size(), ptr(any_vis), ptr(new_index), n,
                                            ptr(o), current_stream()))
             self.launches += 1
             rows_out.append(o)
-        return new_index, kept_off, kept_host, out_off_host, cmask, rows_out
+        return new_index, kept_off, kept_host, (out_off_host if host_sizes else out_off), cmask, rows_out
 
     def seg_tables(self, b: SceneBatch):
         """Instance histograms and the feature-row <-> object binding of every view."""

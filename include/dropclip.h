@@ -190,6 +190,10 @@ DC_API size_t dc_compact_workspace(int64_t total_points);
 DC_API int dc_compact_scan(const uint8_t* any_visible, int64_t total_points, const int64_t* point_off,
                     int n_scenes, int64_t* new_index, int64_t* kept_off, void* workspace,
                     size_t workspace_bytes, dc_stream_t stream);
+/* out_off[n_scenes + 1] = prefix of V_s * N'_s (layout of the compacted mask blocks) computed on the device, so a
+ * device-resident pipeline needs no host round trip between dc_compact_scan and dc_unpack_visibility_compact. */
+DC_API int dc_compact_mask_offsets(const int64_t* kept_off, const int64_t* view_off, int n_scenes, int64_t* out_off,
+                            dc_stream_t stream);
 /* out[new_index[j]] = in[j] for kept rows of `row_bytes` bytes (points, colours, labels, features). */
 DC_API int dc_compact_rows(const void* in, int64_t row_bytes, const uint8_t* any_visible, const int64_t* new_index,
                     int64_t total_points, void* out, dc_stream_t stream);

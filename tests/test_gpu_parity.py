@@ -700,3 +700,24 @@ def test_aggregate_views_blender_new_vs_restatement():
         assert p.shape == wp.shape and p.shape[0] < 3 * 60 * 80
         assert np.array_equal(l, wl)
         assert np.allclose(p, wp, rtol=0, atol=1e-11) and np.allclose(c, wc, rtol=0, atol=1e-12)
+
+
+def test_compact_visibility_without_host_sizes_matches_synced_path():
+    """Device-resident form of the compaction (no read-back of sizes): same masks, layout offsets on the GPU."""
+    from dropclip_b200.engine import FusionEngine, SceneBatch
+    eng = FusionEngine("cuda")
+    scenes = []
+    for name in FUSE[:2]:
+        sc = gio.scene_of(gio.load(name))
+        scenes.append({"points": sc.points, "depths": sc.depths, "camera_poses": sc.camera_poses, "intrinsic": sc.intrinsic,
+                       "inv": sc.inv_poses})
+    b = SceneBatch.from_host(scenes, "cuda", inv_poses=[s["inv"] for s in scenes])
+    records, rank, any_s = eng.visibility_sorted(b, 0.05)
+    _, kept_a, kept_host, out_off_host, cmask_a, rows_a = eng.compact_visibility(b, any_s, records, rank, torch.uint8, [b.points])
+    _, kept_b, none_host, out_off_dev, cmask_b, rows_b = eng.compact_visibility(b, any_s, records, rank, torch.uint8, [b.points],
+                                                                                host_sizes=False)
+    assert none_host is None and torch.equal(kept_a, kept_b)
+    assert np.array_equal(out_off_dev.cpu().numpy(), out_off_host)
+    n_mask, n_kept = int(out_off_host[-1]), int(kept_host[-1])
+    assert cmask_b.numel() >= n_mask and torch.equal(cmask_b[:n_mask], cmask_a)
+    assert torch.equal(rows_b[0][:n_kept], rows_a[0])
