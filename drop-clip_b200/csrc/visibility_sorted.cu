@@ -17,6 +17,8 @@
 //      (V,N) mask rows coalesced - or, fused with the removal of never-visible points, writes the
 //      compacted (V,N') mask directly (the form fuse_obj_prior returns, utils/feature_fusion.py
 //      :277-281), so the full mask never touches HBM.
+#include <mutex>
+
 #include "visibility_math.cuh"
 
 namespace {
@@ -570,6 +572,27 @@ __global__ void __launch_bounds__(kThreads) unpack_kernel(const uint32_t* __rest
 
 
 
+// Serialises the users of c_views on one device: holds a process-wide mutex while work is enqueued, makes the
+// caller's stream wait for the previous user's last kernel, and records the new "last use" event on release.
+struct ConstBankTurn {
+  static constexpr int kMaxDevices = 64;
+  static std::mutex& mutex() { static std::mutex m; return m; }
+  static cudaEvent_t* events() { static cudaEvent_t e[kMaxDevices] = {}; return e; }
+  std::unique_lock<std::mutex> lock;
+  cudaStream_t stream;
+  cudaError_t status = cudaSuccess;
+  int device = 0;
+  explicit ConstBankTurn(cudaStream_t st) : lock(mutex()), stream(st) {
+    status = cudaGetDevice(&device);
+    if (status != cudaSuccess) return;
+    if (device < 0 || device >= kMaxDevices) { status = cudaErrorInvalidDevice; return; }
+    cudaEvent_t& ev = events()[device];
+    if (!ev) status = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    else status = cudaStreamWaitEvent(stream, ev, 0);
+  }
+  cudaError_t release() { return cudaEventRecord(events()[device], stream); }
+};
+
 // scenes per filter launch: bounded by the constant bank and by one full wave of CTAs; balanced
 int64_t scenes_per_group(int n_scenes, int64_t max_points_per_scene, int max_views_per_scene) {
   const int64_t ctas_per_scene = dc::ceil_div<int64_t>(max_points_per_scene, kTile);
@@ -637,6 +660,10 @@ int dc_project_visibility_sorted(const double* points, const int64_t* point_off,
   // stream order. A group is at most one full wave of CTAs.
   const int64_t ctas_per_scene = dc::ceil_div<int64_t>(max_points_per_scene, kTile);
   const int64_t group = scenes_per_group(n_scenes, max_points_per_scene, max_views_per_scene);
+  // The constant bank is one per device: calls on different streams (or from different host threads) take
+  // turns on it. The lock covers the enqueue, the event chain covers the execution on the device.
+  ConstBankTurn turn(st);
+  if (turn.status != cudaSuccess) return dc::fail(DC_ERR_CUDA, "dc_project_visibility_sorted: %s", cudaGetErrorString(turn.status));
   for (int s0 = 0; s0 < n_scenes; s0 += (int)group) {
     const int ns = (int)((n_scenes - s0 < group) ? (n_scenes - s0) : group);
     DC_CUDA(cudaMemcpyToSymbolAsync(c_views, vc + (size_t)s0 * max_views_per_scene,
@@ -652,6 +679,7 @@ int dc_project_visibility_sorted(const double* points, const int64_t* point_off,
     visibility_filter_kernel<<<grid, kThreads, smem, st>>>(p);
   }
   DC_LAUNCH_CHECK();
+  DC_CUDA(turn.release());
   return DC_OK;
 }
 

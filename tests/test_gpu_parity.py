@@ -721,3 +721,40 @@ def test_compact_visibility_without_host_sizes_matches_synced_path():
     n_mask, n_kept = int(out_off_host[-1]), int(kept_host[-1])
     assert cmask_b.numel() >= n_mask and torch.equal(cmask_b[:n_mask], cmask_a)
     assert torch.equal(rows_b[0][:n_kept], rows_a[0])
+
+
+def test_sorted_visibility_concurrent_streams_share_the_constant_bank_safely():
+    """Two host threads on two streams call the sorted pipeline at the same time; the camera tables live in
+    the device's single constant bank, so calls must take turns on it without corrupting each other."""
+    import threading
+    from dropclip_b200.engine import FusionEngine, batch_from_device
+    from dropclip_b200.scenes import make_scene
+    eng = FusionEngine("cuda")
+    batches = [batch_from_device([make_scene(500 + 7 * t + i, n_views=9 + 4 * t, n_points=30_000, n_objects=6, device="cuda",
+                                             as_torch=True) for i in range(3)], "cuda") for t in range(2)]
+    want = []
+    for b in batches:
+        rec, rank, anyv = eng.visibility_sorted(b, 0.05)
+        want.append(eng.unpack_visibility(b, rec, rank, torch.uint8).clone())
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(t):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for _ in range(12):
+                    rec, rank, anyv = eng.visibility_sorted(batches[t], 0.05)
+                    got = eng.unpack_visibility(batches[t], rec, rank, torch.uint8)
+                    stream.synchronize()
+                    if not torch.equal(got, want[t]):
+                        errors.append(t)
+        except Exception as exc:  # pragma: no cover
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors
