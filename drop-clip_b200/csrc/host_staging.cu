@@ -12,6 +12,7 @@
 //     of the reference (IndexError for ids >= Q, quirk q7) is kept.
 // These run on the caller's cores under ctypes (GIL released). They move and narrow bytes; nothing
 // of the fusion arithmetic is evaluated here.
+#include <emmintrin.h>  // SSE2 streaming stores (baseline x86-64)
 #include <stdint.h>
 #include <string.h>
 
@@ -23,6 +24,35 @@
 #include "common.cuh"
 
 namespace {
+
+// Copy into pinned staging memory with non-temporal stores: the destination is read next by the DMA engine,
+// not by a core, so write-allocating it into the caches only adds a read-for-ownership of every line
+// (a third of the DRAM traffic of a plain memcpy at these sizes).
+inline void stream_copy(void* dst, const void* src, size_t len) {
+  char* d = static_cast<char*>(dst);
+  const char* s = static_cast<const char*>(src);
+  const size_t head = ((16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15);
+  if (len < 256 || head > len) {
+    memcpy(d, s, len);
+    return;
+  }
+  memcpy(d, s, head);
+  d += head; s += head; len -= head;
+  size_t n64 = len / 64;
+  for (size_t i = 0; i < n64; ++i) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s));
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 16));
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 32));
+    const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 48));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d), a);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 16), b);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 32), c);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 48), e);
+    s += 64; d += 64;
+  }
+  memcpy(d, s, len - n64 * 64);
+  _mm_sfence();
+}
 
 template <typename F>
 void parallel_items(int64_t n_items, int n_threads, F&& fn) {
@@ -58,7 +88,7 @@ int dc_host_gather_copy(const void* const* srcs, int64_t n_items, int64_t item_b
   parallel_items(n_items * per_item, n_threads, [&](int64_t t) {
     const int64_t i = t / per_item, s = (t - i * per_item) * slice;
     const int64_t len = std::min(slice, item_bytes - s);
-    memcpy(static_cast<char*>(dst) + i * item_bytes + s, static_cast<const char*>(srcs[i]) + s, (size_t)len);
+    stream_copy(static_cast<char*>(dst) + i * item_bytes + s, static_cast<const char*>(srcs[i]) + s, (size_t)len);
   });
   return DC_OK;
 }

@@ -330,6 +330,29 @@ class PinnedStaging:
         return view.to(self.device, non_blocking=True)
 
 
+class _Tick:
+    """Records a (start, end) CUDA event pair for one launch group when the engine's profile is enabled.
+    (A module-level class: building a class object per call leaves cyclic garbage behind, and the collector's
+    pauses showed up as multi-millisecond gaps between launches.)"""
+    __slots__ = ("eng", "name", "a", "b")
+
+    def __init__(self, eng, name):
+        self.eng, self.name = eng, name
+
+    def __enter__(self):
+        if self.eng.profile is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.eng.profile is not None:
+            self.b.record()
+            self.eng.profile.setdefault(self.name, []).append((self.a, self.b))
+        return False
+
+
 class FusionEngine:
     """Launch sequences over a SceneBatch. Every method only enqueues work on the current stream."""
 
@@ -343,23 +366,7 @@ class FusionEngine:
 
     def _tick(self, name: str):
         """Context manager recording CUDA events around a launch group on the current stream."""
-        eng = self
-
-        class _T:
-            def __enter__(self_inner):
-                if eng.profile is not None:
-                    self_inner.a = torch.cuda.Event(enable_timing=True)
-                    self_inner.b = torch.cuda.Event(enable_timing=True)
-                    self_inner.a.record()
-                return self_inner
-
-            def __exit__(self_inner, *exc):
-                if eng.profile is not None:
-                    self_inner.b.record()
-                    eng.profile.setdefault(name, []).append((self_inner.a, self_inner.b))
-                return False
-
-        return _T()
+        return _Tick(self, name)
 
     def profile_ms(self) -> Dict[str, float]:
         """Mean duration per recorded launch group (call after a synchronize)."""
