@@ -14,9 +14,15 @@ def stage(*a, **k):
 def finish(*a, **k):
     t0 = time.perf_counter(); r = orig_finish(*a, **k); log.append(("finish", threading.current_thread().name, (time.perf_counter() - t0) * 1e3)); return r
 M._stage_obj, M._finish_obj = stage, finish
-for rep in range(4):
+def stats():
+    d = torch.cuda.memory_stats()
+    h = torch.cuda.host_memory_stats() if hasattr(torch.cuda, "host_memory_stats") else {}
+    return d["num_device_alloc"], h.get("num_host_alloc", -1)
+for rep in range(8):
     log.clear()
+    s0 = stats()
     t0 = time.perf_counter()
     outs = [(f.cpu(), w.cpu(), vis) for (f, w, vis), _ in M.fuse_many(args, return_obj=True, device="cuda")]
     dt = (time.perf_counter() - t0) * 1e3
-    print(f"rep {rep}: {dt / 4:.1f} ms/scene |", " ".join(f"{k}:{t:.1f}" for k, _, t in log))
+    s1 = stats()
+    print(f"rep {rep}: {dt / 4:.1f} ms/scene | device allocs +{s1[0]-s0[0]} host allocs +{s1[1]-s0[1]} |", " ".join(f"{k}:{t:.1f}" for k, _, t in log))

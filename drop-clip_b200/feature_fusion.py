@@ -297,7 +297,11 @@ class MultiviewFeatureFusion:
             self._many_stagings = [PinnedStaging(dev), PinnedStaging(dev)]  # pinned buffers are expensive: keep them
         stagings = self._many_stagings
         dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
-        side = torch.cuda.Stream(device=dev)
+        # one persistent side stream: the caching allocator keeps a pool per stream, so a fresh stream per call would
+        # cudaMalloc every staging buffer again (measured: +6 device allocations and ~150 ms per call)
+        if getattr(self, "_many_stream", None) is None or self._many_stream.device != torch.device("cuda", dev_index):
+            self._many_stream = torch.cuda.Stream(device=dev)
+        side = self._many_stream
 
         def stage(k, args):
             torch.cuda.set_device(dev_index)
