@@ -441,21 +441,22 @@ class FusionEngine:
             check(self.lib.dc_compact_mask_offsets(ptr(kept_off), ptr(b.off["view"]), b.n_scenes, ptr(out_off), current_stream()))
             self.launches += 1
             mask_elems, n_kept = int(b.off_host["mask"][-1]), n
-        cmask = torch.empty(mask_elems, dtype=out_dtype, device=b.device)
+        cmask_buf = torch.empty(max(mask_elems, 1), dtype=out_dtype, device=b.device)  # empty tensors have a null data_ptr
+        cmask = cmask_buf[:mask_elems]
         with self._tick("unpack_compact"):
             check(self.lib.dc_unpack_visibility_compact(ptr(records), ptr(rank), ptr(b.off["point"]), ptr(b.off["view"]),
                                                         ptr(any_vis), ptr(new_index), ptr(kept_off), ptr(out_off), b.n_scenes, n,
-                                                        max(b.n_points, default=0), ptr(cmask), cmask.element_size(),
+                                                        max(b.n_points, default=0), ptr(cmask_buf), cmask.element_size(),
                                                         current_stream()))
         self.launches += 1
         rows_out = []
         for t in extra_rows:
             t2 = t.reshape(n, -1)
-            o = torch.empty((n_kept, t2.shape[1]), dtype=t.dtype, device=b.device)
+            o_buf = torch.empty((max(n_kept, 1), t2.shape[1]), dtype=t.dtype, device=b.device)
             check(self.lib.dc_compact_rows(ptr(t2), t2.shape[1] * t2.element_size(), ptr(any_vis), ptr(new_index), n,
-                                           ptr(o), current_stream()))
+                                           ptr(o_buf), current_stream()))
             self.launches += 1
-            rows_out.append(o)
+            rows_out.append(o_buf[:n_kept])
         return new_index, kept_off, kept_host, (out_off_host if host_sizes else out_off), cmask, rows_out
 
     def seg_tables(self, b: SceneBatch):
@@ -513,11 +514,13 @@ class FusionEngine:
 
     def scatter_to_points(self, b: SceneBatch, fused, labels, point_off, n_scenes, max_points, skip_first=True):
         dim = int(fused.shape[1])
-        out = torch.empty((int(labels.shape[0]), dim), dtype=torch.float32, device=fused.device)
-        check(self.lib.dc_scatter_to_points(ptr(fused), ptr(b.off["query"]), ptr(labels), ptr(point_off), n_scenes,
-                                            max_points, dim, int(skip_first), ptr(out), current_stream()))
-        self.launches += 1
-        return out
+        n_rows = int(labels.shape[0])
+        out = torch.empty((max(n_rows, 1), dim), dtype=torch.float32, device=fused.device)
+        if n_rows > 0:
+            check(self.lib.dc_scatter_to_points(ptr(fused), ptr(b.off["query"]), ptr(labels), ptr(point_off), n_scenes,
+                                                max_points, dim, int(skip_first), ptr(out), current_stream()))
+            self.launches += 1
+        return out[:n_rows]
 
     # ------------------------------------------------------------------ compaction
     def compact(self, b: SceneBatch, any_vis, mask, extra_rows: Sequence[torch.Tensor] = (), out_dtype=None):
@@ -539,20 +542,22 @@ class FusionEngine:
         widen = out_dtype is not None and out_dtype != mask.dtype
         if widen and not (mask.dtype == torch.uint8 and out_dtype == torch.int64):
             raise ValueError("compact: only uint8 -> int64 widening is supported")
-        cmask = torch.empty(int(out_off_host[-1]), dtype=out_dtype if widen else mask.dtype, device=b.device)
+        n_mask = int(out_off_host[-1])
+        cmask_buf = torch.empty(max(n_mask, 1), dtype=out_dtype if widen else mask.dtype, device=b.device)
         check(self.lib.dc_compact_mask(ptr(mask), 18 if widen else mask.element_size(), ptr(b.off["mask"]), ptr(b.off["point"]),
                                        ptr(b.off["view"]), ptr(any_vis), ptr(new_index), ptr(kept_off), ptr(out_off),
-                                       b.n_scenes, max(b.n_points, default=0), max(b.n_views, default=0), ptr(cmask),
+                                       b.n_scenes, max(b.n_points, default=0), max(b.n_views, default=0), ptr(cmask_buf),
                                        current_stream()))
         self.launches += 1
+        cmask = cmask_buf[:n_mask]
         rows_out = []
         for t in extra_rows:
             t2 = t.reshape(n, -1)
-            o = torch.empty((int(kept_host[-1]), t2.shape[1]), dtype=t.dtype, device=b.device)
+            o_buf = torch.empty((max(int(kept_host[-1]), 1), t2.shape[1]), dtype=t.dtype, device=b.device)
             check(self.lib.dc_compact_rows(ptr(t2), t2.shape[1] * t2.element_size(), ptr(any_vis), ptr(new_index), n,
-                                           ptr(o), current_stream()))
+                                           ptr(o_buf), current_stream()))
             self.launches += 1
-            rows_out.append(o)
+            rows_out.append(o_buf[:int(kept_host[-1])])
         return new_index, kept_off, kept_host, out_off_host, cmask, rows_out
 
     # ------------------------------------------------------------------ whole object-level pass
