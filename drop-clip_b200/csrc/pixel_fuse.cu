@@ -35,6 +35,7 @@ struct PixParams {
   const int64_t* query_off;
   int sim_kernel, norm_feat;
   int height, width;
+  const int64_t* perm;
   float* out_sum;
   float* out_weight;
 };
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_kernel(PixParams p) {
   const uint8_t* vis_scene = p.visible + p.mask_off[scene];
   float* w_scene = p.out_weight ? p.out_weight + p.mask_off[scene] : nullptr;
 
-  for (int64_t i = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); i < n_pts; i += (int64_t)gridDim.x * kWarps) {
+  for (int64_t s_pos = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); s_pos < n_pts; s_pos += (int64_t)gridDim.x * kWarps) {
+    const int64_t i = p.perm ? __ldg(p.perm + p0 + s_pos) : s_pos;  // spatially sorted processing order, original indexing
     const double x = __ldg(p.points + 3 * (p0 + i)), y = __ldg(p.points + 3 * (p0 + i) + 1),
                  z = __ldg(p.points + 3 * (p0 + i) + 2);
     float acc[kMaxPerLane];
@@ -223,7 +225,8 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_vec_kernel(PixParams p) {
   const uint8_t* vis_scene = p.visible + p.mask_off[scene];
   float* w_scene = p.out_weight ? p.out_weight + p.mask_off[scene] : nullptr;
 
-  for (int64_t i = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); i < n_pts; i += (int64_t)gridDim.x * kWarps) {
+  for (int64_t s_pos = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); s_pos < n_pts; s_pos += (int64_t)gridDim.x * kWarps) {
+    const int64_t i = p.perm ? __ldg(p.perm + p0 + s_pos) : s_pos;  // spatially sorted processing order, original indexing
     const double x = __ldg(p.points + 3 * (p0 + i)), y = __ldg(p.points + 3 * (p0 + i) + 1),
                  z = __ldg(p.points + 3 * (p0 + i) + 2);
     float4 acc[kChunks];
@@ -398,7 +401,8 @@ int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t*
                   const double* intrinsics, const int64_t* mask_off, const uint8_t* visible, const void* seg, int seg_dtype,
                   const float* patch_feats, int patch_h, int patch_w, int dim, const float* queries,
                   const int64_t* query_off, int sim_kernel, int norm_feat, int n_scenes, int64_t max_points_per_scene,
-                  int max_views_per_scene, int height, int width, float* out_sum, float* out_weight, dc_stream_t stream) {
+                  int max_views_per_scene, int height, int width, const int64_t* perm, float* out_sum, float* out_weight,
+                  dc_stream_t stream) {
   DC_CHECK_ARG(points && point_off && view_off && inv_poses && intrinsics && mask_off && visible && patch_feats && out_sum,
                "dc_pixel_fuse: null pointer argument");
   DC_CHECK_ARG(sim_kernel >= DC_SIM_NONE && sim_kernel <= DC_SIM_MEAN, "dc_pixel_fuse: Please set method in [mean, max]");
@@ -411,7 +415,7 @@ int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t*
   const size_t smem = ((size_t)max_views_per_scene * 12 + 9) * sizeof(double);
   DC_CHECK_ARG(smem <= 48 * 1024, "dc_pixel_fuse: too many views per scene (%d)", max_views_per_scene);
   PixParams p{points, point_off, view_off, inv_poses, intrinsics, mask_off, visible, seg, seg_dtype, patch_feats, patch_h,
-              patch_w, dim, queries, query_off, sim_kernel, norm_feat, height, width, out_sum, out_weight};
+              patch_w, dim, queries, query_off, sim_kernel, norm_feat, height, width, perm, out_sum, out_weight};
   dim3 grid(blocks_for(max_points_per_scene, n_scenes), (unsigned)n_scenes);
   const bool aligned = (((uintptr_t)patch_feats | (uintptr_t)queries | (uintptr_t)out_sum) & 15) == 0;
   cudaStream_t st = dc::as_stream(stream);

@@ -617,6 +617,37 @@ size_t dc_visibility_sorted_workspace(int64_t total_points, int n_scenes, int ma
   return carve(nullptr, total_points, n_scenes > 0 ? n_scenes : 1, max_views_per_scene).total;
 }
 
+size_t dc_spatial_sort_workspace(int n_scenes) {
+  const size_t ns = (size_t)(n_scenes > 0 ? n_scenes : 1);
+  return ((sizeof(float) * 6 * ns + 255) / 256) * 256 + sizeof(int) * (size_t)kCells * ns;
+}
+
+int dc_spatial_sort(const double* points, const int64_t* point_off, int n_scenes, int64_t total_points,
+                    int64_t max_points_per_scene, int64_t* perm, int64_t* rank, void* workspace, size_t workspace_bytes,
+                    dc_stream_t stream) {
+  DC_CHECK_ARG(points && point_off && perm && rank && workspace, "dc_spatial_sort: null pointer argument");
+  if (n_scenes <= 0 || max_points_per_scene <= 0 || total_points <= 0) return DC_OK;
+  DC_CHECK_ARG(n_scenes <= 65535, "dc_spatial_sort: at most 65535 scenes per call");
+  if (workspace_bytes < dc_spatial_sort_workspace(n_scenes))
+    return dc::fail(DC_ERR_WORKSPACE, "dc_spatial_sort: workspace %zu < %zu", workspace_bytes, dc_spatial_sort_workspace(n_scenes));
+  float* bbox = reinterpret_cast<float*>(workspace);
+  int* counts = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + ((sizeof(float) * 6 * (size_t)n_scenes + 255) / 256) * 256);
+  cudaStream_t st = dc::as_stream(stream);
+  init_bbox_kernel<<<dc::ceil_div(n_scenes * 6, 128), 128, 0, st>>>(bbox, n_scenes);
+  DC_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)kCells * n_scenes, st));
+  int64_t chunks = dc::ceil_div<int64_t>(max_points_per_scene, kThreads * 4);
+  const int64_t cap = dc::ceil_div<int64_t>((int64_t)dc::sm_count() * 8, n_scenes);
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  dim3 g1((unsigned)chunks, (unsigned)n_scenes);
+  bbox_kernel<<<g1, kThreads, 0, st>>>(points, point_off, bbox);
+  cell_count_kernel<<<g1, kThreads, 0, st>>>(points, point_off, bbox, counts);
+  cell_scan_kernel<<<(unsigned)n_scenes, 1024, 0, st>>>(counts);
+  cell_scatter_kernel<<<g1, kThreads, 0, st>>>(points, point_off, bbox, counts, perm, rank);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
 int dc_project_visibility_sorted(const double* points, const int64_t* point_off, const int64_t* view_off, const float* depths,
                                  const float* inv_poses, const double* intrinsics, int n_scenes, int64_t total_points,
                                  int64_t max_points_per_scene, int max_views_per_scene, int height, int width,

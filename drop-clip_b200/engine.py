@@ -578,7 +578,7 @@ class FusionEngine:
         return out
 
     # ------------------------------------------------------------------ pixel-level path
-    def pixel_fuse(self, b: SceneBatch, mask_u8, sim_kernel, norm_feat: bool):
+    def pixel_fuse(self, b: SceneBatch, mask_u8, sim_kernel, norm_feat: bool, spatial_order: bool = True):
         """aggregate_features (utils/feature_fusion.py:138-250): returns (sum_features [sum N, C] f32,
         similarity weights [mask layout] f32 | None). `b.feats` is the (TV, ph, pw, C) patch stack."""
         tv, ph, pw, dim = b.feats.shape
@@ -587,14 +587,27 @@ class FusionEngine:
         weight = torch.empty(int(b.off_host["mask"][-1]), dtype=torch.float32, device=b.device) \
             if kern != _lib.DC_SIM_NONE else None
         segs = b.segs if kern != _lib.DC_SIM_NONE else None
+        perm = self.spatial_sort(b)[0] if spatial_order and b.total_points > 0 else None
         check(self.lib.dc_pixel_fuse(
             ptr(b.points), ptr(b.off["point"]), ptr(b.off["view"]), ptr(b.inv_poses), ptr(b.intrinsics), ptr(b.off["mask"]),
             ptr(mask_u8), ptr(segs), _lib.torch_dtype_code(segs.dtype) if segs is not None else _lib.DC_I64,
             ptr(b.feats), int(ph), int(pw), int(dim), ptr(b.queries) if kern else None,
             ptr(b.off["query"]) if kern else None, kern, int(bool(norm_feat)), b.n_scenes, max(b.n_points, default=0),
-            max(b.n_views, default=0), b.height, b.width, ptr(sums), ptr(weight), current_stream()))
+            max(b.n_views, default=0), b.height, b.width, ptr(perm), ptr(sums), ptr(weight), current_stream()))
         self.launches += 1
         return sums, weight
+
+    def spatial_sort(self, b: SceneBatch):
+        """(perm, rank): counting sort of every scene's points by Morton cell (order inside a cell is arbitrary)."""
+        n = b.total_points
+        perm = torch.empty(max(n, 1), dtype=torch.int64, device=b.device)
+        rank = torch.empty(max(n, 1), dtype=torch.int64, device=b.device)
+        ws_bytes = self.lib.dc_spatial_sort_workspace(b.n_scenes)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=b.device)
+        check(self.lib.dc_spatial_sort(ptr(b.points), ptr(b.off["point"]), b.n_scenes, n, max(b.n_points, default=0), ptr(perm),
+                                       ptr(rank), ptr(ws), ws_bytes, current_stream()))
+        self.launches += 5
+        return perm, rank
 
     def pixel_normalize(self, b: SceneBatch, sums, mask_u8, weight):
         check(self.lib.dc_pixel_normalize(ptr(sums), ptr(b.off["point"]), ptr(b.off["view"]), ptr(b.off["mask"]),

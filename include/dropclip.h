@@ -109,6 +109,13 @@ DC_API int dc_project_visibility_sorted(const double* points, const int64_t* poi
                                  int max_views_per_scene, int height, int width, double threshold,
                                  uint32_t* records, int64_t* rank, uint8_t* any_visible, void* workspace,
                                  size_t workspace_bytes, dc_stream_t stream);
+/* The counting sort by Morton cell on its own: perm[p0 + s] = scene-local index of the point at sorted position s,
+ * rank[p0 + i] = sorted position of point i. Used to give point-major kernels spatially coherent warps
+ * (dc_pixel_fuse takes `perm`). The order inside a cell is arbitrary; consumers must not depend on it. */
+DC_API size_t dc_spatial_sort_workspace(int n_scenes);
+DC_API int dc_spatial_sort(const double* points, const int64_t* point_off, int n_scenes, int64_t total_points,
+                    int64_t max_points_per_scene, int64_t* perm, int64_t* rank, void* workspace,
+                    size_t workspace_bytes, dc_stream_t stream);
 DC_API int dc_unpack_visibility(const uint32_t* records, const int64_t* rank, const int64_t* point_off,
                          const int64_t* view_off, const int64_t* mask_off, int n_scenes, int64_t total_points,
                          int64_t max_points_per_scene, void* mask, int mask_elem_size, dc_stream_t stream);
@@ -216,13 +223,15 @@ DC_API int dc_compact_mask(const void* mask, int elem_size, const int64_t* mask_
  *   visible     [mask layout] uint8 from dc_project_visibility; pixels recomputed internally
  *   out_sum     [total_points, dim] fp32 (sum of weighted features, = sum_features :243)
  *   out_weight  [mask layout] fp32 similarity weights (similarity_mask :238) or NULL
+ *   perm        [total_points] from dc_spatial_sort or NULL: processing order of the points inside a scene
+ *               (neighbouring warps then share bicubic taps in L1); results do not depend on it
  */
 DC_API int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t* view_off,
                   const float* inv_poses, const double* intrinsics, const int64_t* mask_off,
                   const uint8_t* visible, const void* seg, int seg_dtype, const float* patch_feats, int patch_h,
                   int patch_w, int dim, const float* queries, const int64_t* query_off, int sim_kernel,
                   int norm_feat, int n_scenes, int64_t max_points_per_scene, int max_views_per_scene,
-                  int height, int width, float* out_sum, float* out_weight, dc_stream_t stream);
+                  int height, int width, const int64_t* perm, float* out_sum, float* out_weight, dc_stream_t stream);
 /* feat[j,:] = sum[j,:] / denom[j] with denom = sum_v weight (similarity) or sum_v visible. */
 DC_API int dc_pixel_normalize(float* sums, const int64_t* point_off, const int64_t* view_off, const int64_t* mask_off,
                        const uint8_t* visible, const float* weight, int n_scenes, int64_t max_points_per_scene,
