@@ -255,7 +255,14 @@ class PinnedStaging:
 
     @staticmethod
     def _host_threads() -> int:
-        return max(1, min(16, (os.cpu_count() or 1)))
+        """Threads for the host staging helpers: the cores this process may use, shared between the ranks of
+        the node when launched under torchrun (LOCAL_WORLD_SIZE), at most 16 (more does not add bandwidth)."""
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            cores = os.cpu_count() or 1
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        return max(1, min(16, cores // ranks))
 
     def upload_list(self, arrays, dtype: torch.dtype, item_shape, group_bytes: int = 48 << 20,
                     narrow_to_u8: bool = False):

@@ -101,3 +101,39 @@ def test_pixel_level_path_with_a_cloud_that_no_view_sees():
                                       sc.query_embeddings, device="cuda")
     assert tuple(f.shape) == (0, sc.mv_features[0].shape[-1]) and tuple(vis.shape) == (len(sc.depths), 0) and sim is None
     assert p.shape == (0, 3) and c.shape[0] == 0 and l.shape == (0,)
+
+
+def test_full_size_scene_properties():
+    """One MV-TOD-sized scene (73 views, 480x640, 100 k points, 21 objects, 768-d): size-independent properties
+    of the object-level pass - histogram totals and per-id counts, weights from the documented formula range,
+    fused rows equal to the weighted mean of the bound feature rows recomputed in fp64, NaN rows exactly for
+    objects bound in no view, compaction keeps exactly the points visible somewhere."""
+    from dropclip_b200.engine import FusionEngine, batch_from_device
+    from dropclip_b200.scenes import make_scene
+    eng = FusionEngine("cuda")
+    sc = make_scene(777, n_views=73, n_points=100_000, n_objects=21, device="cuda", as_torch=True)
+    b = batch_from_device([sc], "cuda")
+    res = eng.fuse_object_level(b, 0.05, False, True, "max", torch.uint8)
+    counts, outside, row_object, object_row, status = eng.seg_tables(b)
+    V, HW, Q, C = 73, 480 * 640, 21, 768
+    assert int(status.abs().sum()) == 0 and int(outside.sum()) == 0
+    assert torch.equal(counts.sum(1).long(), torch.full((V,), HW, device="cuda"))
+    for v in (0, 36, 72):  # torch.bincount as an independent counter
+        assert torch.equal(counts[v, :Q].long(), torch.bincount(b.segs[v].reshape(-1), minlength=Q)[:Q])
+    w = res["weight_obj"][: Q * V].view(Q, V).double()
+    rows = object_row[: Q * V].view(Q, V).long()
+    assert (w[rows < 0] == 0).all() and (w[rows >= 0] >= 1e-6).all() and (w <= 1.0 + 1e-6).all()  # clip(pos - max neg, 1e-6), sims in [0,1]
+    feats = b.feats.double()
+    gathered = feats[rows.clamp(min=0)] * (rows >= 0).unsqueeze(-1)
+    want = (gathered * w.unsqueeze(-1)).sum(1) / w.sum(1, keepdim=True)
+    got = res["fused"].double()
+    seen = w.sum(1) > 0
+    assert torch.equal(torch.isnan(got).all(1), ~seen) and not bool(seen[0])  # the table (id 0) is never bound (quirk q10)
+    rel = (got[seen] - want[seen]).abs().max() / want[seen].abs().max()
+    assert float(rel) <= 1e-5
+    new_index, kept_off, kept_host, out_off, cmask, _ = eng.compact_visibility(b, res["any_visible"], res["records"], res["rank"],
+                                                                               torch.uint8)
+    full = eng.unpack_visibility(b, res["records"], res["rank"], torch.uint8).view(V, -1)
+    keep = full.sum(0) > 0
+    assert torch.equal(keep, res["any_visible"].bool()) and int(kept_host[-1]) == int(keep.sum())
+    assert torch.equal(cmask.view(V, -1), full[:, keep])
