@@ -257,6 +257,12 @@ def run_ours(args):
             traffic, traffic_src = tj[top]["bytes_per_launch"], tj[top]["source"]
     except Exception:
         pass
+    try:  # what ncu says limits the projection/visibility kernel (it is issue-bound, not HBM-bound)
+        if "project_visibility" in kernels and "limiter" in tj.get("project_visibility", {}):
+            kernels["project_visibility"]["limiter"] = tj["project_visibility"]["limiter"]
+            kernels["project_visibility"]["dram_traffic"] = tj["project_visibility"]["bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": kernels[top]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "share_of_step": kernels[top]["ms"] / ms_step, "kernels": kernels}
