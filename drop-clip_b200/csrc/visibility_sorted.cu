@@ -136,30 +136,44 @@ __global__ void __launch_bounds__(kThreads) cell_count_kernel(const double* __re
     atomicAdd(counts + (int64_t)scene * kCells + cell_of(points, p0 + i, bb), 1);
 }
 
-// one CTA per scene: exclusive scan of its kCells counters, in place
+// one CTA per scene: exclusive scan of its kCells counters, in place. Warp w owns the 1024 consecutive
+// counters [w * 1024, (w + 1) * 1024) and walks them 32 at a time (coalesced), scanning with shuffles;
+// the 32 warp totals are scanned once and added in a second coalesced pass.
 __global__ void __launch_bounds__(1024) cell_scan_kernel(int* __restrict__ counts) {
-  __shared__ int s[1024];
-  int* c = counts + (int64_t)blockIdx.x * kCells;
-  constexpr int per = kCells / 1024;
-  int loc[per], sum = 0;
+  static_assert(kCells == 32 * 1024, "one warp per 1024 counters");
+  __shared__ int s_warp[32];
+  int* c = counts + (int64_t)blockIdx.x * kCells + (threadIdx.x >> 5) * 1024;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int carry = 0;
+#pragma unroll 4
+  for (int it = 0; it < 32; ++it) {
+    const int v = c[it * 32 + lane];
+    int incl = v;
 #pragma unroll
-  for (int k = 0; k < per; ++k) {
-    loc[k] = c[threadIdx.x * per + k];
-    sum += loc[k];
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    c[it * 32 + lane] = carry + incl - v;  // exclusive inside the warp's range
+    carry += __shfl_sync(0xffffffffu, incl, 31);
   }
-  s[threadIdx.x] = sum;
+  if (lane == 0) s_warp[warp] = carry;
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int add = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
-    __syncthreads();
-    s[threadIdx.x] += add;
-    __syncthreads();
-  }
-  int run = s[threadIdx.x] - sum;
+  if (warp == 0) {
+    const int t = s_warp[lane];
+    int incl = t;
 #pragma unroll
-  for (int k = 0; k < per; ++k) {
-    c[threadIdx.x * per + k] = run;
-    run += loc[k];
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    s_warp[lane] = incl - t;
+  }
+  __syncthreads();
+  const int base = s_warp[warp];
+  if (base != 0) {
+#pragma unroll 4
+    for (int it = 0; it < 32; ++it) c[it * 32 + lane] += base;
   }
 }
 
