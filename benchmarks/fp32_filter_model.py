@@ -35,7 +35,9 @@ def run(seed=1234, V=16, N=20000, jitter=0.0):
         # fp32 filter
         P = K @ M  # fp64
         Pf = P.astype(f32)
-        S = np.abs(P[:, :3]) @ B + np.abs(P[:, 3])
+        A = np.stack([np.abs(K[0, 0]) * np.abs(M[0]) + np.abs(K[0, 2]) * np.abs(M[2]),
+                      np.abs(K[1, 1]) * np.abs(M[1]) + np.abs(K[1, 2]) * np.abs(M[2]), np.abs(M[2])])  # no cancellation
+        S = A[:, :3] @ B + A[:, 3]
         E = (C_ERR * EPS * S * (1 + 2.0 ** -20))
         Ex, Ey, Ez = E
         pf = pts.astype(f32)

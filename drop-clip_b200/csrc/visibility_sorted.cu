@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(kThreads) cell_scatter_kernel(const double* __
 //   P = K * [R|t]' (3x4, evaluated once per view in fp64, rows 1,2 of the inverse pose negated),
 //   q~_r = fp32 dot(P~_r, [p~;1]).  Rounding P and p to fp32 costs 2 eps per product, the chain at
 //   most 5 more roundings, the reference's own fp64 roundings ~10 u:  |q~_r - q_r| <= E_r :=
-//   8 eps * (sum_j |P_rj| * B_j + |P_r3|), B = per-scene bound on |coordinate| (from the bbox pass).
+//   8 eps * (sum_j A_rj * B_j + A_r3), A_rj = |K_r0||M_0j| + |K_r2||M_2j| >= |P_rj| (no cancellation, so the
+//   same sum times 8 u also bounds the reference's fp64 roundings), B = per-scene bound on |coordinate|.
 //   r~ = rcp.approx(q~_z) (1 ulp) = (1 + eta) / q_z with |eta| <= rho := 1.03 E_z r~ + 5 eps, valid while
 //   q~_z >= zmin := max(1024 E_z, 4 E_x, 4 E_y)  (points behind or within ~2 cm of the camera plane take
 //   the exact path; then rho <= 1.01e-3 and E_x r~ <= 0.26).   u~ = q~_x * r~  =>
@@ -300,8 +301,18 @@ __global__ void camera_prep_kernel(const float* __restrict__ inv_poses, const do
     }
     const double eps = 5.9604644775390625e-08;  // 2^-24
 #pragma unroll
+    // magnitude sums WITHOUT cancellation between the two products of a row of K * M: they bound the fp32
+    // error of q~ (|P_rj| <= A_rj) and, times 8 u, the rounding of the reference's own two-step fp64 evaluation
+    double A[12];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      A[j] = fabs(K[0]) * fabs(m[j]) + fabs(K[2]) * fabs(m[8 + j]);
+      A[4 + j] = fabs(K[4]) * fabs(m[4 + j]) + fabs(K[5]) * fabs(m[8 + j]);
+      A[8 + j] = fabs(m[8 + j]);
+    }
+#pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const double S = fabs(P[4 * r]) * B[0] + fabs(P[4 * r + 1]) * B[1] + fabs(P[4 * r + 2]) * B[2] + fabs(P[4 * r + 3]);
+      const double S = A[4 * r] * B[0] + A[4 * r + 1] * B[1] + A[4 * r + 2] * B[2] + A[4 * r + 3];
       ok &= S < 1e30;
       E[r] = fmax(8.0 * eps * S * (1.0 + 1e-6), 1e-30);
     }
