@@ -758,3 +758,52 @@ def test_sorted_visibility_concurrent_streams_share_the_constant_bank_safely():
     for th in threads:
         th.join()
     assert not errors
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_sorted_filter_randomised_differential_vs_literal_kernel(seed):
+    """Fuzz: random image sizes, intrinsics (incl. off-centre principal points), thresholds, world scales, cameras
+    pushed into / far out of the cloud, points with heavy outliers - the fp32 filter + exact queue must reproduce
+    the literal fp64 kernel bit for bit on every (point, view), and a sample of views is cross-checked against
+    the C oracle."""
+    from oracle import c_oracle
+    from dropclip_b200.engine import FusionEngine, SceneBatch
+    from dropclip_b200.scenes import small_scene
+    rng = np.random.default_rng(1000 + seed)
+    h, w = int(rng.integers(40, 200)), int(rng.integers(40, 260))
+    sc = small_scene(300 + seed, n_views=int(rng.integers(2, 9)), n_points=int(rng.integers(2000, 30000)), n_objects=6,
+                     height=h, width=w)
+    scale = float(10.0 ** rng.uniform(-2, 3))
+    pts = sc.points * scale
+    out = rng.random(pts.shape[0]) < 0.02
+    pts[out] *= rng.uniform(-50, 50, size=(int(out.sum()), 1))          # outliers far outside every frustum
+    pts[:7] = [np.nan, 0, 0], [np.inf, 1, 1], [1e300, 0, 0], [0, 0, 0], [-1e16, 2, 2], [1e14, 1e14, 1e14], [1e-300, 0, 0]
+    poses = []
+    for v, P in enumerate(sc.camera_poses):
+        P = P.astype(np.float64).copy()
+        P[:3, 3] *= scale
+        if v % 3 == 1:
+            P[:3, 3] *= rng.uniform(0.0, 0.3)      # camera inside the cloud: points near and behind the image plane
+        if v % 3 == 2:
+            P[:3, 3] *= rng.uniform(3, 30)         # far away: everything lands on a few pixels
+        poses.append(P.astype(np.float32))
+        sc.depths[v] = (sc.depths[v].astype(np.float64) * scale).astype(np.float32)
+    intr = dict(sc.intrinsic)
+    intr["fx"] *= rng.uniform(0.3, 3.0)
+    intr["fy"] *= rng.uniform(0.3, 3.0)
+    intr["cx"] += rng.uniform(-0.4 * w, 0.4 * w)
+    intr["cy"] += rng.uniform(-0.4 * h, 0.4 * h)
+    thr = float(rng.choice([0.05, 0.5, 1e-3, 5.0]) * scale)
+    inv = [np.linalg.inv(p) for p in poses]
+    eng = FusionEngine("cuda")
+    b = SceneBatch.from_host([{"points": pts, "depths": sc.depths, "camera_poses": poses, "intrinsic": intr}], "cuda",
+                             inv_poses=[inv])
+    direct, any_d, _ = eng.visibility(b, thr, torch.uint8)
+    rec, rank, any_s = eng.visibility_sorted(b, thr)
+    got = eng.unpack_visibility(b, rec, rank, torch.uint8)
+    assert torch.equal(got, direct) and torch.equal(any_s, any_d)
+    from dropclip_b200.engine import intrinsic_matrix
+    v = int(rng.integers(0, len(poses)))
+    with np.errstate(all="ignore"):
+        want = c_oracle.visibility_view(pts, sc.depths[v], inv[v], intrinsic_matrix(intr), threshold=thr)
+    assert np.array_equal(got.view(len(poses), -1)[v].cpu().numpy().astype(np.int64), want)
