@@ -234,6 +234,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (live CUDA-event durations from the timed region)
     alg = algorithmic_bytes(batch)
+    resident_gb = batch.h2d_bytes() / 1e9  # inputs of the timed step (before the uint8 variant below replaces the maps)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -266,6 +267,36 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": kernels[top]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "share_of_step": kernels[top]["ms"] / ms_step, "kernels": kernels}
+
+    # ---- the same step with the instance maps resident as uint8: this is what the library's own staging
+    # (SceneBatch.from_host -> dc_host_gather_narrow_i64_u8) leaves in HBM for the reference's int64 maps; the
+    # headline `value` above keeps them int64, the dtype the reference hands over
+    alt = None
+    try:
+        del res, comp
+        batch.segs = batch.segs.to(torch.uint8)
+        torch.cuda.empty_cache()
+        res = comp = None
+        for _ in range(max(3, args.warmup)):
+            res, comp = step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            res, comp = step()
+        a1.record()
+        torch.cuda.synchronize()
+        ms_alt = torch.tensor([a0.elapsed_time(a1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms_alt, op=dist.ReduceOp.MAX)
+        ms_alt_step = float(ms_alt.item()) / args.steps
+        alt = {"seg_dtype": "uint8", "ms_per_step": ms_alt_step, "value": world * args.scenes / (ms_alt_step * 1e-3),
+               "unit": "scenes/s", "note": "instance maps narrowed at staging time (1 byte per pixel in HBM)"}
+        del res, comp
+    except Exception as exc:  # never let the supplementary measurement break the contract line
+        alt = {"error": repr(exc)}
 
     # ---- end to end through the reference-shaped host API
     e2e = None
@@ -354,8 +385,9 @@ def run_ours(args):
                        "image": "480x640", "seg_dtype": "int64", "mask_dtype": "uint8", "feature_dtype": "fp16",
                        "flags": "use_obj_prior=1,use_similarity=1,use_visibility=0,sim_kernel=max,return_obj=True",
                        "parallelism": "scene-parallel x%d, no data-path collective; all_gather of fused features" % world,
-                       "l2": "inputs per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (batch.h2d_bytes() / 1e9)},
+                       "l2": "inputs per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % resident_gb},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "resident_uint8_instance_maps": alt,
         }
         print(json.dumps(line))
     if world > 1:
