@@ -43,44 +43,71 @@ __device__ __forceinline__ void push(RunAcc& r, long long id, unsigned* warp_his
 }
 
 template <typename T>
+__device__ __forceinline__ void consume_vector(const int4& raw, RunAcc& run, unsigned* hist, unsigned& outside, int nbins) {
+  constexpr int VEC = VecOf<T>::n;
+  const T* e = reinterpret_cast<const T*>(&raw);
+  if (sizeof(T) < 8) {
+    // narrow ids: a 16-byte vector that repeats one id (the usual case inside an object or on the table)
+    // extends or starts a run with a handful of word compares instead of 16 / 4 element pushes
+    const unsigned first = (unsigned)raw.x;
+    const unsigned pat = sizeof(T) == 1 ? (first & 0xffu) * 0x01010101u : first;
+    if (((unsigned)raw.x == pat) & ((unsigned)raw.y == pat) & ((unsigned)raw.z == pat) & ((unsigned)raw.w == pat)) {
+      const long long id = (long long)e[0];
+      if (id == run.cur) {
+        run.cnt += VEC;
+      } else {
+        flush_run(run, hist, outside, nbins);
+        run.cur = id;
+        run.cnt = VEC;
+      }
+      return;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) push(run, (long long)e[k], hist, outside, nbins);
+}
+
+// One shared-memory histogram per CTA (run-length compression keeps the atomics on it rare), four 128-bit
+// loads in flight per thread.
+template <typename T>
 __global__ void __launch_bounds__(kThreads) seg_histogram_kernel(const T* __restrict__ seg, int64_t pixels_per_view,
                                                                  int nbins, uint32_t* __restrict__ counts,
                                                                  uint32_t* __restrict__ outside_out) {
-  extern __shared__ unsigned s_hist[];  // [kWarps][nbins]
+  extern __shared__ unsigned s_hist[];  // [nbins]
   const int view = blockIdx.y;
-  const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < kWarps * nbins; i += kThreads) s_hist[i] = 0;
+  for (int i = threadIdx.x; i < nbins; i += kThreads) s_hist[i] = 0;
   __syncthreads();
-  unsigned* warp_hist = s_hist + warp * nbins;
   const T* base = seg + (int64_t)view * pixels_per_view;
   constexpr int VEC = VecOf<T>::n;
   // a view may start anywhere: scalar head up to the next 16-byte boundary, 128-bit body, scalar tail
   int64_t head = (int64_t)(((16 - ((uintptr_t)base & 15)) & 15) / sizeof(T));
   if (head > pixels_per_view) head = pixels_per_view;
   const int64_t n_vec = (pixels_per_view - head) / VEC;
-  const T* body = base + head;
+  const int4* body = reinterpret_cast<const int4*>(base + head);
   RunAcc run{-1, 0};
   unsigned outside = 0;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_vec; i += stride) {
-    const int4 raw = dc::ld_stream(reinterpret_cast<const int4*>(body) + i);
-    const T* e = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) push(run, (long long)e[k], warp_hist, outside, nbins);
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  for (; i + 3 * stride < n_vec; i += 4 * stride) {
+    const int4 r0 = dc::ld_stream(body + i), r1 = dc::ld_stream(body + i + stride), r2 = dc::ld_stream(body + i + 2 * stride),
+               r3 = dc::ld_stream(body + i + 3 * stride);
+    consume_vector<T>(r0, run, s_hist, outside, nbins);
+    consume_vector<T>(r1, run, s_hist, outside, nbins);
+    consume_vector<T>(r2, run, s_hist, outside, nbins);
+    consume_vector<T>(r3, run, s_hist, outside, nbins);
   }
+  for (; i < n_vec; i += stride) consume_vector<T>(dc::ld_stream(body + i), run, s_hist, outside, nbins);
   if (blockIdx.x == 0) {
-    for (int64_t i = threadIdx.x; i < head; i += kThreads) push(run, (long long)base[i], warp_hist, outside, nbins);
-    for (int64_t i = head + n_vec * VEC + threadIdx.x; i < pixels_per_view; i += kThreads)
-      push(run, (long long)base[i], warp_hist, outside, nbins);
+    for (int64_t j = threadIdx.x; j < head; j += kThreads) push(run, (long long)base[j], s_hist, outside, nbins);
+    for (int64_t j = head + n_vec * VEC + threadIdx.x; j < pixels_per_view; j += kThreads)
+      push(run, (long long)base[j], s_hist, outside, nbins);
   }
-  flush_run(run, warp_hist, outside, nbins);
+  flush_run(run, s_hist, outside, nbins);
   outside = __reduce_add_sync(0xffffffffu, outside);
   if ((threadIdx.x & 31) == 0 && outside) atomicAdd(outside_out + view, outside);
   __syncthreads();
   for (int b = threadIdx.x; b < nbins; b += kThreads) {
-    unsigned t = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) t += s_hist[w * nbins + b];
+    const unsigned t = s_hist[b];
     if (t) atomicAdd(counts + (int64_t)view * nbins + b, t);
   }
 }
@@ -148,7 +175,7 @@ extern "C" int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_vi
   int64_t cap = dc::ceil_div<int64_t>(vec_per_view, (int64_t)kThreads * 4);
   unsigned gx = (unsigned)max((int64_t)1, min(want, max((int64_t)1, cap)));
   dim3 grid(gx, (unsigned)total_views);
-  const size_t smem = sizeof(unsigned) * kWarps * nbins;
+  const size_t smem = sizeof(unsigned) * nbins;
   if (seg_dtype == DC_U8)
     seg_histogram_kernel<uint8_t><<<grid, kThreads, smem, st>>>((const uint8_t*)seg, pixels_per_view, nbins, counts, outside);
   else if (seg_dtype == DC_I32)
