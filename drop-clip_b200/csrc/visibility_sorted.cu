@@ -183,9 +183,25 @@ __global__ void __launch_bounds__(kThreads) cell_scatter_kernel(const double* __
   const int scene = blockIdx.y;
   const int64_t p0 = point_off[scene], n = point_off[scene + 1] - p0;
   const float* bb = bbox + scene * 6;
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-    const int pos = atomicAdd(counts + (int64_t)scene * kCells + cell_of(points, p0 + i, bb), 1);
-    perm[p0 + pos] = i;   // order inside a cell depends on scheduling; results do not (they are un-permuted)
+  int* c = counts + (int64_t)scene * kCells;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  // four returning atomics in flight per thread: the slot reservation is a round trip to L2
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    int cell[4], pos[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cell[k] = cell_of(points, p0 + i + k * stride, bb);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pos[k] = atomicAdd(c + cell[k], 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      perm[p0 + pos[k]] = i + k * stride;  // order inside a cell depends on scheduling; results do not (they are un-permuted)
+      rank[p0 + i + k * stride] = pos[k];
+    }
+  }
+  for (; i < n; i += stride) {
+    const int pos = atomicAdd(c + cell_of(points, p0 + i, bb), 1);
+    perm[p0 + pos] = i;
     rank[p0 + i] = pos;
   }
 }
