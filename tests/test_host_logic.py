@@ -202,3 +202,20 @@ def test_host_staging_helpers_copy_and_narrow():
                                                         ctypes.byref(bad)))
             assert bad.value == 1
     assert lib.dc_host_gather_copy(None, 1, 4, None, 1) != 0  # null pointers are rejected, not dereferenced
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """profiles/r01_bench_final.json is a line printed by bench.py on a B200; its shape is the driver's contract."""
+    import json
+    path = os.path.join(ROOT, "profiles", "r01_bench_final.json")
+    d = json.loads(open(path).read())
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["metric"] == "fused_scenes_per_sec" and d["unit"] == "scenes/s" and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] in ("port", "reference")
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert d["gpu_launches"] > 0 and {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
