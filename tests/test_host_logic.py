@@ -4,6 +4,7 @@ import os
 import re
 import subprocess
 import sys
+import time
 
 import numpy as np
 import pytest
@@ -219,3 +220,36 @@ def test_committed_bench_line_has_the_contract_keys():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] in ("port", "reference")
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
     assert d["gpu_launches"] > 0 and {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+
+
+def test_host_staging_pool_survives_fork():
+    """The staging helpers keep a persistent worker pool; a forked child (multiprocessing 'fork') has none of the
+    parent's threads and must rebuild it instead of waiting for workers that do not exist."""
+    import ctypes
+    import numpy as np
+    from dropclip_b200 import _lib
+    lib = _lib.load()
+    arrs = [np.full(5000, i, dtype=np.float32) for i in range(40)]
+    srcs = (ctypes.c_void_p * 40)(*[a.ctypes.data for a in arrs])
+    dst = np.empty((40, 5000), dtype=np.float32)
+    assert lib.dc_host_gather_copy(srcs, 40, 20000, ctypes.c_void_p(dst.ctypes.data), 8) == 0
+    pid = os.fork()
+    if pid == 0:
+        ok = 1
+        try:
+            out = np.empty((40, 5000), dtype=np.float32)
+            rc = lib.dc_host_gather_copy(srcs, 40, 20000, ctypes.c_void_p(out.ctypes.data), 8)
+            ok = 0 if (rc == 0 and np.array_equal(out, np.stack(arrs))) else 2
+        finally:
+            os._exit(ok)
+    deadline = time.time() + 30
+    while time.time() < deadline:
+        done, status = os.waitpid(pid, os.WNOHANG)
+        if done:
+            assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+            break
+        time.sleep(0.05)
+    else:
+        os.kill(pid, 9)
+        raise AssertionError("forked child hung in the staging helper")
+    assert np.array_equal(dst, np.stack(arrs))
