@@ -320,7 +320,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        n_e2e = max(2, min(args.steps, 5))
+        n_e2e = max(2, min(args.steps, 10))
         up0 = M._staging.bytes_uploaded
         t0 = time.perf_counter()
         for _ in range(n_e2e):

@@ -272,7 +272,7 @@ class PinnedStaging:
         ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
         return max(1, min(16, cores // ranks))
 
-    def upload_list(self, arrays, dtype: torch.dtype, item_shape, group_bytes: int = 16 << 20,
+    def upload_list(self, arrays, dtype: torch.dtype, item_shape, group_bytes: int = int(os.environ.get("DC_UPLOAD_GROUP_MB", "32")) << 20,
                     narrow_to_u8: bool = False):
         """Stacks a list of equally-shaped host arrays straight into one pinned buffer and uploads it
         group by group, so the H2D copy of group g overlaps the host copy of group g+1. Contiguous
