@@ -458,7 +458,7 @@ __device__ __forceinline__ void stage_project(const ViewConst& c, const FastPara
   cp_async_commit();
 }
 
-__global__ void __launch_bounds__(kThreads, 2) visibility_filter_kernel(const __grid_constant__ FastParams p) {
+__global__ void __launch_bounds__(kThreads, 3) visibility_filter_kernel(const __grid_constant__ FastParams p) {
   extern __shared__ uint32_t s_dyn[];  // [n_words][kTile] records, [8][kQueue] queues, [3][kTile] gathered depths
   const int scene = p.scene0 + blockIdx.y;
   const int64_t p0 = p.point_off[scene];
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, 2) visibility_filter_kernel(const __
   int qcount = 0;
 
   // stage B of view v: depth test on the gathers issued three stages earlier, queue pushes, record flush
-  auto stage_test = [&](int v, const float (&qz)[kPts], const float* __restrict__ s_slot) {
+  auto stage_test = [&](int v, const float (&qz)[kPts], const float* __restrict__ s_slot) -> bool {
     const uint32_t bit = 1u << (v & 31);
     const float thr_lo = cviews[v].thr_lo, thr_hi = cviews[v].thr_hi;
     cp_async_wait<2>();  // all but the two most recent groups have landed
@@ -522,13 +522,6 @@ __global__ void __launch_bounds__(kThreads, 2) visibility_filter_kernel(const __
         if (mine) s_queue[qcount + __popc(b & ((1u << lane) - 1u))] = ((uint32_t)v << 12) | (uint32_t)(k * kThreads + threadIdx.x);
         qcount += __popc(b);
       }
-      if (qcount > kQueue - 32 * kPts) {
-        __syncwarp();
-        drain_queue(s_queue, qcount, n_tile, p.points + 3 * p0, p.perm + p0 + tile0, p.inv_poses + v0 * 16,
-                    p.intrinsics + (int64_t)scene * 9, p.depths + v0 * hw, p.width, p.height, p.threshold, s_rec);
-        __syncwarp();
-        qcount = 0;
-      }
     }
     if ((v & 31) == 31 || v == n_views - 1) {
 #pragma unroll
@@ -537,34 +530,45 @@ __global__ void __launch_bounds__(kThreads, 2) visibility_filter_kernel(const __
         word[k] = 0;
       }
     }
+    return qcount > kQueue - 32 * kPts;  // no room for another view's worth of entries: the caller drains
   };
 
   // Three gather groups rotate (the loop is unrolled by three): the gathers of view v + 3 are issued
   // right after view v has been tested, two views of arithmetic before they are needed - enough to
   // cover a DRAM miss. Every stage commits exactly one (possibly empty) group, so "all but the two
   // most recent groups" always names the view under test.
+  // The exact queue is drained outside the pipelined loop (one call site, no call inside the hot loop): when
+  // it fills up, the pipeline is abandoned after the current view, the queue is resolved, and the pipeline
+  // restarts at the next view (re-issuing at most two views of gathers - rare: ~0.4 % of the pairs are queued).
   float qa[kPts], qb[kPts], qc[kPts];
   float* const sa = s_sensor;
   float* const sb = s_sensor + kTile;
   float* const sc = s_sensor + 2 * kTile;
-  if (n_views > 0) stage_project(cviews[0], p, depth, x, y, z, qa, sa); else cp_async_commit();
-  if (n_views > 1) stage_project(cviews[1], p, depth + hw, x, y, z, qb, sb); else cp_async_commit();
-  if (n_views > 2) stage_project(cviews[2], p, depth + 2 * hw, x, y, z, qc, sc); else cp_async_commit();
-  depth += 3 * hw;
-  for (int v = 0; v < n_views; v += 3, depth += 3 * hw) {
-    stage_test(v, qa, sa);
-    if (v + 3 < n_views) stage_project(cviews[v + 3], p, depth, x, y, z, qa, sa); else cp_async_commit();
-    if (v + 1 < n_views) stage_test(v + 1, qb, sb);
-    if (v + 4 < n_views) stage_project(cviews[v + 4], p, depth + hw, x, y, z, qb, sb); else cp_async_commit();
-    if (v + 2 < n_views) stage_test(v + 2, qc, sc);
-    if (v + 5 < n_views) stage_project(cviews[v + 5], p, depth + 2 * hw, x, y, z, qc, sc); else cp_async_commit();
+  int v_begin = 0;
+  for (;;) {
+    const float* d = depth + (int64_t)v_begin * hw;
+    if (v_begin < n_views) stage_project(cviews[v_begin], p, d, x, y, z, qa, sa); else cp_async_commit();
+    if (v_begin + 1 < n_views) stage_project(cviews[v_begin + 1], p, d + hw, x, y, z, qb, sb); else cp_async_commit();
+    if (v_begin + 2 < n_views) stage_project(cviews[v_begin + 2], p, d + 2 * hw, x, y, z, qc, sc); else cp_async_commit();
+    d += 3 * hw;
+    bool full = false;
+    for (int v = v_begin; v < n_views; v += 3, d += 3 * hw) {
+      if (stage_test(v, qa, sa)) { v_begin = v + 1; full = true; break; }
+      if (v + 3 < n_views) stage_project(cviews[v + 3], p, d, x, y, z, qa, sa); else cp_async_commit();
+      if (v + 1 < n_views && stage_test(v + 1, qb, sb)) { v_begin = v + 2; full = true; break; }
+      if (v + 4 < n_views) stage_project(cviews[v + 4], p, d + hw, x, y, z, qb, sb); else cp_async_commit();
+      if (v + 2 < n_views && stage_test(v + 2, qc, sc)) { v_begin = v + 3; full = true; break; }
+      if (v + 5 < n_views) stage_project(cviews[v + 5], p, d + 2 * hw, x, y, z, qc, sc); else cp_async_commit();
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+    if (qcount > 0)
+      drain_queue(s_queue, qcount, n_tile, p.points + 3 * p0, p.perm + p0 + tile0, p.inv_poses + v0 * 16,
+                  p.intrinsics + (int64_t)scene * 9, p.depths + v0 * hw, p.width, p.height, p.threshold, s_rec);
+    __syncwarp();
+    qcount = 0;
+    if (!full || v_begin >= n_views) break;
   }
-  cp_async_wait<0>();
-  __syncwarp();
-  if (qcount > 0)
-    drain_queue(s_queue, qcount, n_tile, p.points + 3 * p0, p.perm + p0 + tile0, p.inv_poses + v0 * 16,
-                p.intrinsics + (int64_t)scene * 9, p.depths + v0 * hw, p.width, p.height, p.threshold, s_rec);
-  __syncwarp();
 #pragma unroll
   for (int k = 0; k < kPts; ++k) {
     const int local = k * kThreads + threadIdx.x;
