@@ -51,7 +51,7 @@ def parse():
 class ClockSampler:
     """SM clock and throttle reasons sampled in-process through NVML while the step loop runs.
     (An external `nvidia-smi -lms 20` poller was measured to slow the kernels by ~1.6x; NVML calls
-    from a Python thread every 50 ms do not.)"""
+    from a Python thread every 10 ms do not.)"""
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
@@ -78,7 +78,7 @@ class ClockSampler:
                 for k, m in names.items():
                     if bits & m:
                         self.reasons.add(k)
-                self._stop.wait(0.05)
+                self._stop.wait(0.01)
         except Exception as exc:  # pragma: no cover - NVML missing
             self.error = repr(exc)
 
@@ -199,7 +199,7 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()  # samples every 50 ms through warm-up and the timed region (same load)
+        sampler.start()  # samples every 10 ms through warm-up and the timed region (same load)
     # Results stay referenced across steps exactly like in the timed loop below: the host runs ahead of the GPU
     # (the step has no sync), so two generations of outputs are alive at a time and the caching allocator must
     # own both before timing starts (a cudaMalloc of the 467 MB mask inside the timed region costs 20-150 ms).
