@@ -552,7 +552,17 @@ __global__ void __launch_bounds__(kThreads, 3) visibility_filter_kernel(const __
     if (v_begin + 2 < n_views) stage_project(cviews[v_begin + 2], p, d + 2 * hw, x, y, z, qc, sc); else cp_async_commit();
     d += 3 * hw;
     bool full = false;
-    for (int v = v_begin; v < n_views; v += 3, d += 3 * hw) {
+    int v = v_begin;
+    // steady state: six more views exist, no bounds checks on the stages
+    for (; v + 5 < n_views; v += 3, d += 3 * hw) {
+      if (stage_test(v, qa, sa)) { v_begin = v + 1; full = true; break; }
+      stage_project(cviews[v + 3], p, d, x, y, z, qa, sa);
+      if (stage_test(v + 1, qb, sb)) { v_begin = v + 2; full = true; break; }
+      stage_project(cviews[v + 4], p, d + hw, x, y, z, qb, sb);
+      if (stage_test(v + 2, qc, sc)) { v_begin = v + 3; full = true; break; }
+      stage_project(cviews[v + 5], p, d + 2 * hw, x, y, z, qc, sc);
+    }
+    for (; !full && v < n_views; v += 3, d += 3 * hw) {
       if (stage_test(v, qa, sa)) { v_begin = v + 1; full = true; break; }
       if (v + 3 < n_views) stage_project(cviews[v + 3], p, d, x, y, z, qa, sa); else cp_async_commit();
       if (v + 1 < n_views && stage_test(v + 1, qb, sb)) { v_begin = v + 2; full = true; break; }
