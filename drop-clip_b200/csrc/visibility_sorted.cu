@@ -18,6 +18,7 @@
 //      compacted (V,N') mask directly (the form fuse_obj_prior returns, utils/feature_fusion.py
 //      :277-281), so the full mask never touches HBM.
 #include <mutex>
+#include <type_traits>
 
 #include "visibility_math.cuh"
 
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, 3) visibility_filter_kernel(const __
   int qcount = 0;
 
   // stage B of view v: depth test on the gathers issued three stages earlier, queue pushes, record flush
-  auto stage_test = [&](int v, const float (&qz)[kPts], const float* __restrict__ s_slot) -> bool {
+  auto stage_test = [&](auto may_be_last, int v, const float (&qz)[kPts], const float* __restrict__ s_slot) -> bool {
     const uint32_t bit = 1u << (v & 31);
     const float thr_lo = cviews[v].thr_lo, thr_hi = cviews[v].thr_hi;
     cp_async_wait<2>();  // all but the two most recent groups have landed
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, 3) visibility_filter_kernel(const __
         qcount += __popc(b);
       }
     }
-    if ((v & 31) == 31 || v == n_views - 1) {
+    if ((v & 31) == 31 || (decltype(may_be_last)::value && v == n_views - 1)) {
 #pragma unroll
       for (int k = 0; k < kPts; ++k) {
         s_rec[(v >> 5) * kTile + k * kThreads + threadIdx.x] |= word[k];  // warp-private slots: no race with drain's atomicOr
@@ -555,19 +556,19 @@ __global__ void __launch_bounds__(kThreads, 3) visibility_filter_kernel(const __
     int v = v_begin;
     // steady state: six more views exist, no bounds checks on the stages
     for (; v + 5 < n_views; v += 3, d += 3 * hw) {
-      if (stage_test(v, qa, sa)) { v_begin = v + 1; full = true; break; }
+      if (stage_test(std::false_type{}, v, qa, sa)) { v_begin = v + 1; full = true; break; }
       stage_project(cviews[v + 3], p, d, x, y, z, qa, sa);
-      if (stage_test(v + 1, qb, sb)) { v_begin = v + 2; full = true; break; }
+      if (stage_test(std::false_type{}, v + 1, qb, sb)) { v_begin = v + 2; full = true; break; }
       stage_project(cviews[v + 4], p, d + hw, x, y, z, qb, sb);
-      if (stage_test(v + 2, qc, sc)) { v_begin = v + 3; full = true; break; }
+      if (stage_test(std::false_type{}, v + 2, qc, sc)) { v_begin = v + 3; full = true; break; }
       stage_project(cviews[v + 5], p, d + 2 * hw, x, y, z, qc, sc);
     }
     for (; !full && v < n_views; v += 3, d += 3 * hw) {
-      if (stage_test(v, qa, sa)) { v_begin = v + 1; full = true; break; }
+      if (stage_test(std::true_type{}, v, qa, sa)) { v_begin = v + 1; full = true; break; }
       if (v + 3 < n_views) stage_project(cviews[v + 3], p, d, x, y, z, qa, sa); else cp_async_commit();
-      if (v + 1 < n_views && stage_test(v + 1, qb, sb)) { v_begin = v + 2; full = true; break; }
+      if (v + 1 < n_views && stage_test(std::true_type{}, v + 1, qb, sb)) { v_begin = v + 2; full = true; break; }
       if (v + 4 < n_views) stage_project(cviews[v + 4], p, d + hw, x, y, z, qb, sb); else cp_async_commit();
-      if (v + 2 < n_views && stage_test(v + 2, qc, sc)) { v_begin = v + 3; full = true; break; }
+      if (v + 2 < n_views && stage_test(std::true_type{}, v + 2, qc, sc)) { v_begin = v + 3; full = true; break; }
       if (v + 5 < n_views) stage_project(cviews[v + 5], p, d + 2 * hw, x, y, z, qc, sc); else cp_async_commit();
     }
     cp_async_wait<0>();
