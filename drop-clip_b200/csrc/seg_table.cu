@@ -112,46 +112,51 @@ __global__ void __launch_bounds__(kThreads) seg_histogram_kernel(const T* __rest
   }
 }
 
-// One thread per view: ids present (ascending) minus the smallest -> rows 0,1,2,...
-__global__ void view_table_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ outside,
-                                  const int64_t* __restrict__ feat_off, const int32_t* __restrict__ view_scene,
-                                  const int64_t* __restrict__ view_off, const int64_t* __restrict__ query_off,
-                                  const int64_t* __restrict__ wobj_off, int64_t total_views, int nbins,
-                                  int32_t* __restrict__ row_object, int32_t* __restrict__ object_row,
-                                  int32_t* __restrict__ view_status) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per view: ids present (ascending) minus the smallest -> rows 0,1,2,... A lane looks at one bin of
+// each 32-bin chunk and ballots give the ascending rank of every present id. Present ids are ascending, so every
+// id below n_q is preceded only by ids below n_q: its row is simply its rank minus one (the dropped smallest id).
+// (The one-thread-per-view version walked the 256 bins with dependent loads: 36 us for 4672 views.)
+__global__ void __launch_bounds__(128) view_table_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ outside,
+                                                         const int64_t* __restrict__ feat_off, const int32_t* __restrict__ view_scene,
+                                                         const int64_t* __restrict__ view_off, const int64_t* __restrict__ query_off,
+                                                         const int64_t* __restrict__ wobj_off, int64_t total_views, int nbins,
+                                                         int32_t* __restrict__ row_object, int32_t* __restrict__ object_row,
+                                                         int32_t* __restrict__ view_status) {
+  const int64_t g = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (g >= total_views) return;
+  const int lane = threadIdx.x & 31;
   const int s = view_scene[g];
   const int n_q = (int)(query_off[s + 1] - query_off[s]);
   const int n_v = (int)(view_off[s + 1] - view_off[s]);
   const int v_local = (int)(g - view_off[s]);
   const int64_t r0 = feat_off[g];
   const int64_t n_rows = feat_off[g + 1] - r0;
-  int status = 0;
-  if (outside[g]) status |= 1;  // an id outside [0,nbins): cannot be indexed by the reference either
+  int status = outside[g] ? 1 : 0;  // an id outside [0,nbins): cannot be indexed by the reference either
   const uint32_t* c = counts + g * nbins;
-  int64_t next = -1;  // -1: still waiting for the smallest id, which is dropped
-  for (int id = 0; id < nbins; ++id) {
-    if (c[id] == 0) continue;
-    if (next < 0) {
-      next = 0;
-      continue;
+  int seen = 0;   // present ids met so far, the dropped smallest one included
+  int bound = 0;  // rows bound by this lane
+  for (int id0 = 0; id0 < nbins; id0 += 32) {
+    const int id = id0 + lane;
+    const bool present = id < nbins && c[id] != 0;
+    const unsigned mask = __ballot_sync(0xffffffffu, present);
+    if (present) {
+      const int64_t row = (int64_t)seen + __popc(mask & ((1u << lane) - 1u)) - 1;
+      if (row >= 0) {  // row < 0: the smallest present id, dropped like np.unique(seg)[1:]
+        if (id >= n_q) status |= 1;
+        else if (row >= n_rows) status |= 2;
+        else {
+          row_object[r0 + row] = id;
+          object_row[wobj_off[s] + (int64_t)id * n_v + v_local] = (int32_t)(r0 + row);
+          ++bound;
+        }
+      }
     }
-    if (id >= n_q) {
-      status |= 1;
-      continue;
-    }
-    if (next >= n_rows) {
-      status |= 2;
-      continue;
-    }
-    row_object[r0 + next] = id;
-    object_row[wobj_off[s] + (int64_t)id * n_v + v_local] = (int32_t)(r0 + next);
-    ++next;
+    seen += __popc(mask);
   }
-  if (next < 0) next = 0;
-  for (int64_t r = next; r < n_rows; ++r) row_object[r0 + r] = -1;
-  view_status[g] = status;
+  status = __reduce_or_sync(0xffffffffu, status);
+  const int next = __reduce_add_sync(0xffffffffu, bound);
+  for (int64_t r = next + lane; r < n_rows; r += 32) row_object[r0 + r] = -1;  // feature rows no id is bound to
+  if (lane == 0) view_status[g] = status;
 }
 
 }  // namespace
@@ -198,8 +203,8 @@ extern "C" int dc_view_table(const uint32_t* counts, const uint32_t* outside, co
   cudaStream_t st = dc::as_stream(stream);
   if (total_wobj > 0) DC_CUDA(cudaMemsetAsync(object_row, 0xFF, sizeof(int32_t) * (size_t)total_wobj, st));
   (void)total_rows;
-  const int threads = 128;
-  view_table_kernel<<<(unsigned)dc::ceil_div<int64_t>(total_views, threads), threads, 0, st>>>(
+  const int threads = 128;  // four views per CTA, one warp each
+  view_table_kernel<<<(unsigned)dc::ceil_div<int64_t>(total_views, threads / 32), threads, 0, st>>>(
       counts, outside, feat_off, view_scene, view_off, query_off, wobj_off, total_views, nbins, row_object,
       object_row, view_status);
   DC_LAUNCH_CHECK();
