@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_rank_kernel(const uint8_t* 
                                                                  const int64_t* __restrict__ block_sums,
                                                                  int64_t* __restrict__ new_index) {
   __shared__ int s_warp[kScanThreads / 32];
+  __shared__ int s_rank[kScanBlock];  // block-local exclusive ranks, staged so that the 8-byte stores are coalesced
   const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * kScanItems;
   int f[kScanItems];
   int c = 0;
@@ -271,11 +272,19 @@ __global__ void __launch_bounds__(kScanThreads) scan_rank_kernel(const uint8_t* 
   __syncthreads();
   int warp_base = 0;
   for (int w = 0; w < warp; ++w) warp_base += s_warp[w];
-  int64_t run = block_sums[blockIdx.x] + warp_base + (incl - c);
+  int run = warp_base + (incl - c);
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    if (base + k < n) new_index[base + k] = run;
+    s_rank[threadIdx.x * kScanItems + k] = run;
     run += f[k];
+  }
+  __syncthreads();
+  const int64_t block_base = block_sums[blockIdx.x];
+  const int64_t first = (int64_t)blockIdx.x * kScanBlock;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int j = k * kScanThreads + threadIdx.x;  // consecutive lanes -> consecutive elements
+    if (first + j < n) new_index[first + j] = block_base + s_rank[j];
   }
 }
 
