@@ -44,10 +44,12 @@ SIGNATURES = {
     "dc_compact_rows": (c_int, [P, c_int64, P, P, c_int64, P, P]),
     "dc_compact_mask": (c_int, [P, c_int, P, P, P, P, P, P, P, c_int, c_int64, c_int, P, P]),
     "dc_pixel_fuse": (c_int, [P, P, P, P, P, P, P, P, c_int, P, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int64,
-                              c_int, c_int, c_int, P, P, P, P]),
+                              c_int, c_int, c_int, P, P, P, c_int, c_int64, c_int, P, c_size_t, P]),
+    "dc_pixel_fuse_workspace": (c_size_t, [c_int64, c_int, c_int, c_int]),
     "dc_spatial_sort_workspace": (c_size_t, [c_int]),
     "dc_spatial_sort": (c_int, [P, P, c_int, c_int64, c_int64, P, P, P, c_size_t, P]),
     "dc_pixel_normalize": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, P]),
+    "dc_view_clip_gather": (c_int, [P, c_int64, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "dc_voxelize_workspace": (c_size_t, [c_int64]),
     "dc_voxelize": (c_int, [P, P, c_int, c_int64, c_float, P, ctypes.c_int32, P, P, P, P, P, P, c_size_t, P]),
     "dc_voxel_gather": (c_int, [P, c_int64, P, P, P, c_int, c_int64, P, P]),

@@ -11,6 +11,9 @@
 //
 // Bicubic weights follow ATen's upsample_bicubic2d (align_corners=False, A=-0.75, source index
 // scale*(dst+0.5)-0.5 un-clamped, taps clamped to the border).
+#include <algorithm>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -38,6 +41,9 @@ struct PixParams {
   const int64_t* perm;
   float* out_sum;
   float* out_weight;
+  float* dots;   // [total_views][ph * pw][q_stride]: patch row . query, see patch_query_dots_kernel
+  int q_stride;
+  int normalize;  // divide the sums by sum_v weight (similarity) or by the number of views that see the point
 };
 
 __device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
@@ -64,6 +70,86 @@ __device__ __forceinline__ int seg_at(const void* seg, int dtype, int64_t idx) {
   return (v < 0 || v > 0x7fffffff) ? -1 : (int)v;
 }
 
+// The similarity of an interpolated feature with a query is linear in the taps:
+//   f . q = sum_t w_t (T_t . q),   f = sum_t w_t T_t  (16 bicubic taps T_t of the patch map)
+// so the (patch cell, query) dot products are computed ONCE per view (ph * pw * Q dots, 16 M FMA at 24x32x21x768)
+// instead of Q x C FMA and 64 KB of query reads per visible (point, view). The normalisation of `norm_feat`
+// divides the similarity by |f| afterwards ((f / |f|) . q = (f . q) / |f|). Warp per patch cell, lanes over channels.
+__global__ void __launch_bounds__(kThreads) patch_query_dots_kernel(PixParams p) {
+  const int scene = blockIdx.y;
+  const int64_t v0 = p.view_off[scene];
+  const int n_views = (int)(p.view_off[scene + 1] - v0);
+  const int n_q = (int)(p.query_off[scene + 1] - p.query_off[scene]);
+  const float* q = p.queries + p.query_off[scene] * p.dim;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_cells = (int64_t)p.ph * p.pw, n_rows = n_cells * n_views;
+  for (int64_t r = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); r < n_rows; r += (int64_t)gridDim.x * kWarps) {
+    const float* row = p.patch + (v0 * n_cells + r) * p.dim;
+    float* out = p.dots + (v0 * n_cells + r) * p.q_stride;
+    float t[kMaxPerLane];
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) t[k] = (k * 32 + lane < p.dim) ? __ldg(row + k * 32 + lane) : 0.f;
+    for (int o = 0; o < n_q; o += 4) {  // four queries per round: their loads overlap (the kernel is latency-bound)
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (o + j < n_q) {
+          const float* qo = q + (int64_t)(o + j) * p.dim;
+#pragma unroll
+          for (int k = 0; k < kMaxPerLane; ++k)
+            if (k * 32 + lane < p.dim) d[j] = fmaf(t[k], __ldg(qo + k * 32 + lane), d[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[j] = dc::warp_sum(d[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (lane == 0 && o + j < n_q) out[o + j] = d[j];
+    }
+  }
+}
+
+// Similarity weight of one visible (point, view) from the dot table, in two phases. interp_dot: lane l interpolates
+// query o0 + l's dots with the same 16 bicubic weights as the feature (issued BEFORE the tap loads, so the tap
+// coordinates are dead once the feature is formed). finish_weight: divides by |f| under norm_feat and returns
+// clip(pos - max|mean(neg), 1e-6) (calculate_sim, feature_fusion.py:65-73). Scenes with more than 32 queries
+// take further rounds of interp_dot inside finish_weight.
+__device__ __forceinline__ float interp_dot(const PixParams& p, const float* __restrict__ dots_view, const int (&iy)[4],
+                                            const int (&ix)[4], const float (&wy)[4], const float (&wx)[4], int o, int n_q) {
+  float mine = 0.f;
+  if (o < n_q) {
+#pragma unroll
+    for (int ty = 0; ty < 4; ++ty) {
+      const float* row = dots_view + ((int64_t)iy[ty] * p.pw) * p.q_stride + o;
+      const float r = __ldg(row + ix[0] * p.q_stride) * wx[0] + __ldg(row + ix[1] * p.q_stride) * wx[1] +
+                      __ldg(row + ix[2] * p.q_stride) * wx[2] + __ldg(row + ix[3] * p.q_stride) * wx[3];
+      mine = fmaf(r, wy[ty], mine);
+    }
+  }
+  return mine;
+}
+
+template <typename More>
+__device__ __forceinline__ float finish_weight(const PixParams& p, float first, float nrm, int id, int n_q, int lane, More&& more) {
+  float pos = 0.f, red = (p.sim_kernel == DC_SIM_MAX) ? -INFINITY : 0.f;
+  bool nan_seen = false;
+  for (int o0 = 0; o0 < n_q; o0 += 32) {
+    const int o = o0 + lane;
+    float mine = o0 == 0 ? first : more(o);
+    if (p.norm_feat) mine = mine / nrm;
+    if (id >= o0 && id < o0 + 32) pos = __shfl_sync(0xffffffffu, mine, id - o0);
+    const bool is_neg = o < n_q && o != id;
+    nan_seen |= __any_sync(0xffffffffu, is_neg && (mine != mine));
+    if (p.sim_kernel == DC_SIM_MAX) red = fmaxf(red, dc::warp_max(is_neg ? mine : -INFINITY));
+    else red += dc::warp_sum(is_neg ? mine : 0.f);
+  }
+  if (p.sim_kernel == DC_SIM_MEAN) red = red / (float)(n_q - 1);
+  if (nan_seen) red = __int_as_float(0x7fc00000);
+  float weight = pos - red;
+  if (weight == weight) weight = fmaxf(weight, 1e-6f);
+  return weight;
+}
+
 __global__ void __launch_bounds__(kThreads) pixel_fuse_kernel(PixParams p) {
   extern __shared__ double s_cam[];  // [n_views][12] + [9]
   const int scene = blockIdx.y;
@@ -82,7 +168,6 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_kernel(PixParams p) {
   const int lane = threadIdx.x & 31;
   const int per_lane = p.dim / 32;  // host guarantees dim % 32 == 0, dim <= 1024
   const int n_q = p.sim_kernel != DC_SIM_NONE ? (int)(p.query_off[scene + 1] - p.query_off[scene]) : 0;
-  const float* q = p.sim_kernel != DC_SIM_NONE ? p.queries + p.query_off[scene] * p.dim : nullptr;
   const float scale_y = (float)p.ph / (float)p.height, scale_x = (float)p.pw / (float)p.width;
   const int64_t hw = (int64_t)p.height * p.width;
   const uint8_t* vis_scene = p.visible + p.mask_off[scene];
@@ -121,6 +206,8 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_kernel(PixParams p) {
       cubic_taps(pv, scale_y, p.ph, iy, wy);
       cubic_taps(pu, scale_x, p.pw, ix, wx);
       const float* pm = p.patch + (v0 + v) * (int64_t)p.ph * p.pw * p.dim;
+      const float* dots_view = p.dots + (v0 + v) * (int64_t)p.ph * p.pw * p.q_stride;
+      const float first_dot = p.sim_kernel != DC_SIM_NONE ? interp_dot(p, dots_view, iy, ix, wy, wx, lane, n_q) : 0.f;
       float f[kMaxPerLane];
 #pragma unroll
       for (int k = 0; k < kMaxPerLane; ++k) f[k] = 0.f;
@@ -141,12 +228,13 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_kernel(PixParams p) {
           }
         }
       }
+      float nrm = 1.f;
       if (p.norm_feat) {
         float ss = 0.f;
 #pragma unroll
         for (int k = 0; k < kMaxPerLane; ++k)
           if (k < per_lane) ss = fmaf(f[k], f[k], ss);
-        const float nrm = sqrtf(dc::warp_sum(ss));
+        nrm = sqrtf(dc::warp_sum(ss));
 #pragma unroll
         for (int k = 0; k < kMaxPerLane; ++k)
           if (k < per_lane) f[k] = f[k] / nrm;
@@ -155,28 +243,8 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_kernel(PixParams p) {
       if (p.sim_kernel != DC_SIM_NONE) {
         const int id = seg_at(p.seg, p.seg_dtype, (v0 + v) * hw + (int64_t)pv * p.width + pu);
         weight = 0.f;  // pixels whose id has no query keep metric 0 (quirk q13)
-        if (id >= 0 && id < n_q) {
-          float pos = 0.f, red = (p.sim_kernel == DC_SIM_MAX) ? -INFINITY : 0.f;
-          bool nan_seen = false;
-          for (int o = 0; o < n_q; ++o) {
-            const float* qo = q + (int64_t)o * p.dim;
-            float d = 0.f;
-#pragma unroll
-            for (int k = 0; k < kMaxPerLane; ++k)
-              if (k < per_lane) d = fmaf(f[k], __ldg(qo + k * 32 + lane), d);
-            d = dc::warp_sum(d);
-            if (o == id) pos = d;
-            else {
-              nan_seen |= (d != d);
-              if (p.sim_kernel == DC_SIM_MAX) red = fmaxf(red, d);
-              else red += d;
-            }
-          }
-          if (p.sim_kernel == DC_SIM_MEAN) red = red / (float)(n_q - 1);
-          if (nan_seen) red = __int_as_float(0x7fc00000);
-          weight = pos - red;
-          if (weight == weight) weight = fmaxf(weight, 1e-6f);
-        }
+        if (id >= 0 && id < n_q)
+          weight = finish_weight(p, first_dot, nrm, id, n_q, lane, [&](int o) { return interp_dot(p, dots_view, iy, ix, wy, wx, o, n_q); });
         if (w_scene && lane == 0) w_scene[(int64_t)v * n_pts + i] = weight;
 #pragma unroll
         for (int k = 0; k < kMaxPerLane; ++k)
@@ -196,12 +264,11 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_kernel(PixParams p) {
 
 // Same arithmetic with 128-bit accesses: a lane owns 4 consecutive channels of every 128-channel chunk
 // (dim = 128 * kChunks; CLIP ViT-L/14: 6 chunks), which cuts the load instructions per visible
-// (point, view) from 16 * dim / 32 to 16 * dim / 128, and the Q per-query warp reductions (5 shuffles
-// each) are replaced by one transposed reduction of up to 32 partial dot products (31 shuffles),
-// after which lane o holds query o's similarity. The round-1 profile had this kernel at ~1 % of the
-// fp32 peak, bound by the latency of 900 dependent 4-byte loads per lane and pair.
+// (point, view) from 16 * dim / 32 to 16 * dim / 128. The query similarities come from the per-view dot table
+// (pixel_weight), so the kernel reads 49 KB of taps per pair and no queries (the first version read the Q x C query
+// matrix per pair as well: 114 KB of L1 traffic and 16 k extra FMA per pair, ncu: L1 data pipe 58 %, long-scoreboard 4.9/issue).
 template <int kChunks>
-__global__ void __launch_bounds__(kThreads) pixel_fuse_vec_kernel(PixParams p) {
+__global__ void __launch_bounds__(kThreads, 2) pixel_fuse_vec_kernel(PixParams p) {
   extern __shared__ double s_cam[];  // [n_views][12] + [9]
   const int scene = blockIdx.y;
   const int64_t p0 = p.point_off[scene];
@@ -219,7 +286,6 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_vec_kernel(PixParams p) {
   constexpr int kDim = 128 * kChunks;
   const int lane = threadIdx.x & 31;
   const int n_q = p.sim_kernel != DC_SIM_NONE ? (int)(p.query_off[scene + 1] - p.query_off[scene]) : 0;
-  const float4* q4 = p.sim_kernel != DC_SIM_NONE ? reinterpret_cast<const float4*>(p.queries + p.query_off[scene] * kDim) : nullptr;
   const float scale_y = (float)p.ph / (float)p.height, scale_x = (float)p.pw / (float)p.width;
   const int64_t hw = (int64_t)p.height * p.width;
   const uint8_t* vis_scene = p.visible + p.mask_off[scene];
@@ -257,6 +323,8 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_vec_kernel(PixParams p) {
       cubic_taps(pv, scale_y, p.ph, iy, wy);
       cubic_taps(pu, scale_x, p.pw, ix, wx);
       const float4* pm = reinterpret_cast<const float4*>(p.patch + (v0 + v) * (int64_t)p.ph * p.pw * kDim);
+      const float* dots_view = p.dots + (v0 + v) * (int64_t)p.ph * p.pw * p.q_stride;
+      const float first_dot = p.sim_kernel != DC_SIM_NONE ? interp_dot(p, dots_view, iy, ix, wy, wx, lane, n_q) : 0.f;
       float4 f[kChunks];
 #pragma unroll
       for (int k = 0; k < kChunks; ++k) f[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -277,11 +345,12 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_vec_kernel(PixParams p) {
           f[k].w = fmaf(a.w * wx[0] + b.w * wx[1] + c.w * wx[2] + d.w * wx[3], wy[ty], f[k].w);
         }
       }
+      float nrm = 1.f;
       if (p.norm_feat) {
         float ss = 0.f;
 #pragma unroll
         for (int k = 0; k < kChunks; ++k) ss = fmaf(f[k].x, f[k].x, fmaf(f[k].y, f[k].y, fmaf(f[k].z, f[k].z, fmaf(f[k].w, f[k].w, ss))));
-        const float nrm = sqrtf(dc::warp_sum(ss));
+        nrm = sqrtf(dc::warp_sum(ss));
 #pragma unroll
         for (int k = 0; k < kChunks; ++k) {
           f[k].x = f[k].x / nrm;
@@ -294,47 +363,8 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_vec_kernel(PixParams p) {
       if (p.sim_kernel != DC_SIM_NONE) {
         const int id = seg_at(p.seg, p.seg_dtype, (v0 + v) * hw + (int64_t)pv * p.width + pu);
         weight = 0.f;  // pixels whose id has no query keep metric 0 (quirk q13)
-        if (id >= 0 && id < n_q) {
-          float pos = 0.f, red = (p.sim_kernel == DC_SIM_MAX) ? -INFINITY : 0.f;
-          bool nan_seen = false;
-          for (int o0 = 0; o0 < n_q; o0 += 32) {
-            float d[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              d[j] = 0.f;
-              if (o0 + j < n_q) {  // warp-uniform
-                const float4* qo = q4 + (int64_t)(o0 + j) * (kDim / 4) + lane;
-#pragma unroll
-                for (int k = 0; k < kChunks; ++k) {
-                  const float4 t = __ldg(qo + k * 32);
-                  d[j] = fmaf(f[k].x, t.x, fmaf(f[k].y, t.y, fmaf(f[k].z, t.z, fmaf(f[k].w, t.w, d[j]))));
-                }
-              }
-            }
-            // transposed reduction: afterwards lane l holds the full dot product of query o0 + l
-#pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) {
-#pragma unroll
-              for (int j = 0; j < s; ++j) {
-                const bool upper = (lane & s) != 0;
-                const float send = upper ? d[j] : d[j + s];
-                const float keep = upper ? d[j + s] : d[j];
-                d[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-              }
-            }
-            const float mine = d[0];
-            const int o = o0 + lane;
-            if (id >= o0 && id < o0 + 32) pos = __shfl_sync(0xffffffffu, mine, id - o0);
-            const bool is_neg = o < n_q && o != id;
-            nan_seen |= __any_sync(0xffffffffu, is_neg && (mine != mine));
-            if (p.sim_kernel == DC_SIM_MAX) red = fmaxf(red, dc::warp_max(is_neg ? mine : -INFINITY));
-            else red += dc::warp_sum(is_neg ? mine : 0.f);
-          }
-          if (p.sim_kernel == DC_SIM_MEAN) red = red / (float)(n_q - 1);
-          if (nan_seen) red = __int_as_float(0x7fc00000);
-          weight = pos - red;
-          if (weight == weight) weight = fmaxf(weight, 1e-6f);
-        }
+        if (id >= 0 && id < n_q)
+          weight = finish_weight(p, first_dot, nrm, id, n_q, lane, [&](int o) { return interp_dot(p, dots_view, iy, ix, wy, wx, o, n_q); });
         if (w_scene && lane == 0) w_scene[(int64_t)v * n_pts + i] = weight;
 #pragma unroll
         for (int k = 0; k < kChunks; ++k) {  // feat2d[ys,xs] * metric, then +=  (two roundings)
@@ -357,6 +387,186 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_vec_kernel(PixParams p) {
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) dst[k * 32] = acc[k];
   }
+}
+
+// Tile variant of the 128-bit kernel: a CTA owns kTilePts consecutive points of the (Morton-sorted) processing
+// order and walks the views IN STEP (one barrier per view that sees any of them). Neighbouring points project into
+// the same patch cells of a view, so while the CTA is on view v its warps keep hitting the same ~50 KB of taps in
+// L1. The point-major kernel above lets every warp drift through the views at its own pace: the ncu capture of
+// round 1 showed 43 % L1 hits, 10 GB of L2 reads per 8-view scene and 6.6 long-scoreboard stall cycles per issue.
+// The per-point accumulators live in shared memory (kTilePts x dim fp32) so that the visible points of a view can
+// be dealt to the warps round-robin whatever their position in the tile; a point is touched by one warp per view
+// and the barrier orders the views, so every row is accumulated in view order exactly like `sum_features[mask] +=`.
+constexpr int kTilePts = 32;
+
+template <int kChunks>
+__global__ void __launch_bounds__(kThreads, 2) pixel_fuse_tile_kernel(PixParams p) {
+  extern __shared__ double s_cam[];  // [n_views][12] + [9], then the accumulators
+  constexpr int kDim = 128 * kChunks;
+  const int scene = blockIdx.y;
+  const int64_t p0 = p.point_off[scene];
+  const int64_t n_pts = p.point_off[scene + 1] - p0;
+  const int64_t v0 = p.view_off[scene];
+  const int n_views = (int)(p.view_off[scene + 1] - v0);
+  const int64_t tile0 = (int64_t)blockIdx.x * kTilePts;
+  if (tile0 >= n_pts) return;
+  const int n_tile = (int)min((int64_t)kTilePts, n_pts - tile0);
+  for (int i = threadIdx.x; i < n_views * 12; i += kThreads) {
+    const int v = i / 12, e = i - v * 12;
+    s_cam[i] = (double)__ldg(p.inv_poses + (v0 + v) * 16 + e);
+  }
+  double* s_K = s_cam + n_views * 12;
+  if (threadIdx.x < 9) s_K[threadIdx.x] = __ldg(p.intrinsics + (int64_t)scene * 9 + threadIdx.x);
+  float4* s_acc = reinterpret_cast<float4*>(s_cam + (((size_t)n_views * 12 + 9 + 1) & ~(size_t)1));  // 16-byte aligned
+  float* s_den = reinterpret_cast<float*>(s_acc + kTilePts * (kDim / 4));  // [kTilePts] denominators of fuse_points :266-268
+  for (int i = threadIdx.x; i < kTilePts * (kDim / 4); i += kThreads) s_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x < kTilePts) s_den[threadIdx.x] = 0.f;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_q = p.sim_kernel != DC_SIM_NONE ? (int)(p.query_off[scene + 1] - p.query_off[scene]) : 0;
+  const float scale_y = (float)p.ph / (float)p.height, scale_x = (float)p.pw / (float)p.width;
+  const int64_t hw = (int64_t)p.height * p.width;
+  const uint8_t* vis_scene = p.visible + p.mask_off[scene];
+  float* w_scene = p.out_weight ? p.out_weight + p.mask_off[scene] : nullptr;
+  // lane l <-> tile slot l: original index of the point at sorted position tile0 + l
+  const int64_t my_i = lane < n_tile ? (p.perm ? __ldg(p.perm + p0 + tile0 + lane) : tile0 + lane) : 0;
+  const double px = __ldg(p.points + 3 * (p0 + my_i)), py = __ldg(p.points + 3 * (p0 + my_i) + 1), pz = __ldg(p.points + 3 * (p0 + my_i) + 2);
+
+  for (int v = 0; v < n_views; ++v) {
+    const bool vis = lane < n_tile && vis_scene[(int64_t)v * n_pts + my_i] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, vis);  // identical in every warp of the CTA
+    if (m == 0) continue;
+    const int n_vis = __popc(m);
+    const float4* pm = reinterpret_cast<const float4*>(p.patch + (v0 + v) * (int64_t)p.ph * p.pw * kDim);
+    const float* dots_view = p.dots + (v0 + v) * (int64_t)p.ph * p.pw * p.q_stride;
+    // lane-parallel projection: every lane projects ITS slot's point once per view (the same fp64 arithmetic as
+    // visibility.cu; the point is visible, so it is inside); the pair loop below fetches pixels by shuffle
+    const double* cam = s_cam + v * 12;
+    int my_pu = 0, my_pv = 0;
+    {
+      double cx = __dadd_rn(cam[3], __fma_rn(cam[2], pz, __fma_rn(cam[1], py, __dmul_rn(cam[0], px))));
+      double cy = __dadd_rn(cam[7], __fma_rn(cam[6], pz, __fma_rn(cam[5], py, __dmul_rn(cam[4], px))));
+      double cz = __dadd_rn(cam[11], __fma_rn(cam[10], pz, __fma_rn(cam[9], py, __dmul_rn(cam[8], px))));
+      cy = -cy;
+      cz = -cz;
+      const double qx = __fma_rn(s_K[2], cz, __fma_rn(s_K[1], cy, __dmul_rn(s_K[0], cx)));
+      const double qy = __fma_rn(s_K[5], cz, __fma_rn(s_K[4], cy, __dmul_rn(s_K[3], cx)));
+      const double qz = __fma_rn(s_K[8], cz, __fma_rn(s_K[7], cy, __dmul_rn(s_K[6], cx)));
+      if (vis && qz != 0.0) {
+        my_pu = (int)__ddiv_rn(qx, qz);
+        my_pv = (int)__ddiv_rn(qy, qz);
+      }
+    }
+    for (int k = warp; k < n_vis; k += kWarps) {
+      const int slot = __fns(m, 0, k + 1);
+      const int64_t i = __shfl_sync(0xffffffffu, my_i, slot);
+      const int pu = __shfl_sync(0xffffffffu, my_pu, slot), pv = __shfl_sync(0xffffffffu, my_pv, slot);
+      int iy[4], ix[4];
+      float wy[4], wx[4];
+      cubic_taps(pv, scale_y, p.ph, iy, wy);
+      cubic_taps(pu, scale_x, p.pw, ix, wx);
+      // the instance id and the first round of query dots are requested before the taps: both are cold loads whose
+      // latency then hides behind the 96 tap loads instead of sitting in front of the accumulator update
+      const int id = p.sim_kernel != DC_SIM_NONE ? seg_at(p.seg, p.seg_dtype, (v0 + v) * hw + (int64_t)pv * p.width + pu) : -1;
+      const float first_dot = p.sim_kernel != DC_SIM_NONE ? interp_dot(p, dots_view, iy, ix, wy, wx, lane, n_q) : 0.f;
+      // Chunk-major: the 16 taps of one 128-channel chunk are requested back to back (16 independent 128-bit loads
+      // in flight per lane) and folded in the ATen order (along x inside each row, then along y); finished chunks
+      // occupy 4 registers each, so the loads of the next chunk have room without spilling.
+      float4 f[kChunks];
+      int row_off[4], col_off[4];
+#pragma unroll
+      for (int t4 = 0; t4 < 4; ++t4) {
+        row_off[t4] = iy[t4] * p.pw * (kDim / 4) + lane;
+        col_off[t4] = ix[t4] * (kDim / 4);
+      }
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        float4 t[4][4];
+#pragma unroll
+        for (int ty = 0; ty < 4; ++ty)
+#pragma unroll
+          for (int tx = 0; tx < 4; ++tx) t[ty][tx] = __ldg(pm + (row_off[ty] + col_off[tx] + c * 32));
+        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ty = 0; ty < 4; ++ty) {
+          acc4.x = fmaf(t[ty][0].x * wx[0] + t[ty][1].x * wx[1] + t[ty][2].x * wx[2] + t[ty][3].x * wx[3], wy[ty], acc4.x);
+          acc4.y = fmaf(t[ty][0].y * wx[0] + t[ty][1].y * wx[1] + t[ty][2].y * wx[2] + t[ty][3].y * wx[3], wy[ty], acc4.y);
+          acc4.z = fmaf(t[ty][0].z * wx[0] + t[ty][1].z * wx[1] + t[ty][2].z * wx[2] + t[ty][3].z * wx[3], wy[ty], acc4.z);
+          acc4.w = fmaf(t[ty][0].w * wx[0] + t[ty][1].w * wx[1] + t[ty][2].w * wx[2] + t[ty][3].w * wx[3], wy[ty], acc4.w);
+        }
+        f[c] = acc4;
+      }
+      float nrm = 1.f;
+      if (p.norm_feat) {
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) ss = fmaf(f[c].x, f[c].x, fmaf(f[c].y, f[c].y, fmaf(f[c].z, f[c].z, fmaf(f[c].w, f[c].w, ss))));
+        nrm = sqrtf(dc::warp_sum(ss));
+        // one correctly rounded reciprocal and 4 * kChunks multiplications instead of as many IEEE divisions (8-10
+        // instructions each): the quotients differ from `feat2d /= norm` by at most 1 ulp, far inside the 1e-3 bar
+        const float inv = __frcp_rn(nrm);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          f[c].x = f[c].x * inv;
+          f[c].y = f[c].y * inv;
+          f[c].z = f[c].z * inv;
+          f[c].w = f[c].w * inv;
+        }
+      }
+      float4* acc = s_acc + slot * (kDim / 4) + lane;
+      if (p.sim_kernel != DC_SIM_NONE) {
+        float weight = 0.f;  // pixels whose id has no query keep metric 0 (quirk q13)
+        if (id >= 0 && id < n_q)
+          weight = finish_weight(p, first_dot, nrm, id, n_q, lane, [&](int o) { return interp_dot(p, dots_view, iy, ix, wy, wx, o, n_q); });
+        if (w_scene && lane == 0) w_scene[(int64_t)v * n_pts + i] = weight;
+        if (lane == 0) s_den[slot] += weight;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {  // feat2d[ys,xs] * metric, then +=  (two roundings)
+          float4 a = acc[c * 32];
+          a.x += f[c].x * weight;
+          a.y += f[c].y * weight;
+          a.z += f[c].z * weight;
+          a.w += f[c].w * weight;
+          acc[c * 32] = a;
+        }
+      } else {
+        if (lane == 0) s_den[slot] += 1.f;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          float4 a = acc[c * 32];
+          a.x += f[c].x;
+          a.y += f[c].y;
+          a.z += f[c].z;
+          a.w += f[c].w;
+          acc[c * 32] = a;
+        }
+      }
+    }
+    __syncthreads();  // the next view may hand a point to another warp
+  }
+  for (int slot = warp; slot < n_tile; slot += kWarps) {
+    const int64_t i = __shfl_sync(0xffffffffu, my_i, slot);
+    float4* dst = reinterpret_cast<float4*>(p.out_sum + (p0 + i) * kDim) + lane;
+    const float den = s_den[slot];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      float4 a = s_acc[slot * (kDim / 4) + c * 32 + lane];
+      if (p.normalize) a = make_float4(a.x / den, a.y / den, a.z / den, a.w / den);
+      dst[c * 32] = a;
+    }
+  }
+}
+
+// similarity_mask entries of invisible (point, view) pairs are 0 (:238 writes visible pairs only into a zero tensor).
+// The tile kernel writes the visible ones; this pass fills the rest with coalesced stores (the point-major kernels
+// write them from inside their view loop, which in Morton order is one scattered 4-byte store per pair).
+__global__ void __launch_bounds__(kThreads) zero_invisible_weights_kernel(const uint8_t* __restrict__ visible,
+                                                                          const int64_t* __restrict__ mask_off,
+                                                                          float* __restrict__ weight) {
+  const int64_t begin = mask_off[blockIdx.y], end = mask_off[blockIdx.y + 1];
+  for (int64_t j = begin + (int64_t)blockIdx.x * kThreads + threadIdx.x; j < end; j += (int64_t)gridDim.x * kThreads)
+    if (!visible[j]) weight[j] = 0.f;
 }
 
 // feat[j,:] /= denom[j], denom = sum_v weight[v,j] (similarity) or sum_v visible[v,j]
@@ -386,6 +596,77 @@ __global__ void __launch_bounds__(kThreads) pixel_normalize_kernel(float* __rest
   }
 }
 
+// generate_view_clip (data/dataset_blender.py:132-171): every point of a cloud is projected into ONE view
+// (fp64 pose - the json world_matrix is inverted in fp64 there -, truncation toward zero, pixel (0,0) when the
+// projected z is 0), the pixel is CLIPPED into the image instead of tested (:158-159), and the bicubically
+// upsampled patch feature of that pixel is gathered (:151-156,165). No visibility, no weights. The reference
+// materialises the (h, w, C) map per view; here the 16 taps are evaluated per point. Warp per (point, view);
+// lanes stride over channels in float4 when the rows allow it.
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads) view_clip_gather_kernel(const double* __restrict__ points, int64_t n_pts,
+                                                                    const double* __restrict__ inv_poses,
+                                                                    const double* __restrict__ intrinsics,
+                                                                    const float* __restrict__ patch, int ph, int pw, int dim,
+                                                                    int height, int width, float* __restrict__ out) {
+  const int view = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const double* m = inv_poses + (int64_t)view * 16;
+  const double* K = intrinsics;
+  const float scale_y = (float)ph / (float)height, scale_x = (float)pw / (float)width;
+  const float* pm = patch + (int64_t)view * ph * pw * dim;
+  for (int64_t i = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); i < n_pts; i += (int64_t)gridDim.x * kWarps) {
+    const double x = __ldg(points + 3 * i), y = __ldg(points + 3 * i + 1), z = __ldg(points + 3 * i + 2);
+    const double cx = __dadd_rn(__ldg(m + 3), __fma_rn(__ldg(m + 2), z, __fma_rn(__ldg(m + 1), y, __dmul_rn(__ldg(m), x))));
+    const double cy = -__dadd_rn(__ldg(m + 7), __fma_rn(__ldg(m + 6), z, __fma_rn(__ldg(m + 5), y, __dmul_rn(__ldg(m + 4), x))));
+    const double cz = -__dadd_rn(__ldg(m + 11), __fma_rn(__ldg(m + 10), z, __fma_rn(__ldg(m + 9), y, __dmul_rn(__ldg(m + 8), x))));
+    const double qx = __fma_rn(__ldg(K + 2), cz, __fma_rn(__ldg(K + 1), cy, __dmul_rn(__ldg(K), cx)));
+    const double qy = __fma_rn(__ldg(K + 5), cz, __fma_rn(__ldg(K + 4), cy, __dmul_rn(__ldg(K + 3), cx)));
+    const double qz = __fma_rn(__ldg(K + 8), cz, __fma_rn(__ldg(K + 7), cy, __dmul_rn(__ldg(K + 6), cx)));
+    int pu = 0, pv = 0;
+    if (qz != 0.0) {
+      // fp64 -> int64 assignment: truncation; NaN, +-inf and anything beyond int64 become INT64_MIN, which np.clip turns into 0
+      const double uq = __ddiv_rn(qx, qz), vq = __ddiv_rn(qy, qz);
+      if (fabs(uq) < 9.2e18) pu = (int)max(0ll, min((long long)(width - 1), __double2ll_rz(uq)));
+      if (fabs(vq) < 9.2e18) pv = (int)max(0ll, min((long long)(height - 1), __double2ll_rz(vq)));
+    }
+    int iy[4], ix[4];
+    float wy[4], wx[4];
+    cubic_taps(pv, scale_y, ph, iy, wy);
+    cubic_taps(pu, scale_x, pw, ix, wx);
+    float* row_out = out + ((int64_t)view * n_pts + i) * dim;
+    if (kVec) {
+      for (int c = lane; c < dim / 4; c += 32) {
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ty = 0; ty < 4; ++ty) {
+          const float* row = pm + (int64_t)iy[ty] * pw * dim;
+          const float4 a = __ldg(reinterpret_cast<const float4*>(row + (int64_t)ix[0] * dim) + c);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(row + (int64_t)ix[1] * dim) + c);
+          const float4 d = __ldg(reinterpret_cast<const float4*>(row + (int64_t)ix[2] * dim) + c);
+          const float4 e = __ldg(reinterpret_cast<const float4*>(row + (int64_t)ix[3] * dim) + c);
+          f.x = fmaf(a.x * wx[0] + b.x * wx[1] + d.x * wx[2] + e.x * wx[3], wy[ty], f.x);
+          f.y = fmaf(a.y * wx[0] + b.y * wx[1] + d.y * wx[2] + e.y * wx[3], wy[ty], f.y);
+          f.z = fmaf(a.z * wx[0] + b.z * wx[1] + d.z * wx[2] + e.z * wx[3], wy[ty], f.z);
+          f.w = fmaf(a.w * wx[0] + b.w * wx[1] + d.w * wx[2] + e.w * wx[3], wy[ty], f.w);
+        }
+        __stcs(reinterpret_cast<float4*>(row_out) + c, f);  // written once, never re-read here
+      }
+    } else {
+      for (int c = lane; c < dim; c += 32) {
+        float f = 0.f;
+#pragma unroll
+        for (int ty = 0; ty < 4; ++ty) {
+          const float* row = pm + (int64_t)iy[ty] * pw * dim + c;
+          const float r = __ldg(row + (int64_t)ix[0] * dim) * wx[0] + __ldg(row + (int64_t)ix[1] * dim) * wx[1] +
+                          __ldg(row + (int64_t)ix[2] * dim) * wx[2] + __ldg(row + (int64_t)ix[3] * dim) * wx[3];
+          f = fmaf(r, wy[ty], f);
+        }
+        row_out[c] = f;
+      }
+    }
+  }
+}
+
 unsigned blocks_for(int64_t max_points, int n_scenes) {
   int64_t want = dc::ceil_div<int64_t>(max_points, kWarps);
   int64_t cap = dc::ceil_div<int64_t>((int64_t)dc::sm_count() * 16, n_scenes);
@@ -393,15 +674,23 @@ unsigned blocks_for(int64_t max_points, int n_scenes) {
   return (unsigned)(want < 1 ? 1 : want);
 }
 
+int query_stride(int max_queries) { return (max_queries + 7) & ~7; }  // whole 32-byte sectors per (cell) row
+
 }  // namespace
 
 extern "C" {
+
+size_t dc_pixel_fuse_workspace(int64_t total_views, int patch_h, int patch_w, int max_queries_per_scene) {
+  if (total_views <= 0 || patch_h <= 0 || patch_w <= 0 || max_queries_per_scene <= 0) return 0;
+  return (size_t)total_views * patch_h * patch_w * query_stride(max_queries_per_scene) * sizeof(float);
+}
 
 int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t* view_off, const float* inv_poses,
                   const double* intrinsics, const int64_t* mask_off, const uint8_t* visible, const void* seg, int seg_dtype,
                   const float* patch_feats, int patch_h, int patch_w, int dim, const float* queries,
                   const int64_t* query_off, int sim_kernel, int norm_feat, int n_scenes, int64_t max_points_per_scene,
                   int max_views_per_scene, int height, int width, const int64_t* perm, float* out_sum, float* out_weight,
+                  int normalize, int64_t total_views, int max_queries_per_scene, void* workspace, size_t workspace_bytes,
                   dc_stream_t stream) {
   DC_CHECK_ARG(points && point_off && view_off && inv_poses && intrinsics && mask_off && visible && patch_feats && out_sum,
                "dc_pixel_fuse: null pointer argument");
@@ -415,14 +704,56 @@ int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t*
   const size_t smem = ((size_t)max_views_per_scene * 12 + 9) * sizeof(double);
   DC_CHECK_ARG(smem <= 48 * 1024, "dc_pixel_fuse: too many views per scene (%d)", max_views_per_scene);
   PixParams p{points, point_off, view_off, inv_poses, intrinsics, mask_off, visible, seg, seg_dtype, patch_feats, patch_h,
-              patch_w, dim, queries, query_off, sim_kernel, norm_feat, height, width, perm, out_sum, out_weight};
+              patch_w, dim, queries, query_off, sim_kernel, norm_feat, height, width, perm, out_sum, out_weight, nullptr, 0, normalize};
   dim3 grid(blocks_for(max_points_per_scene, n_scenes), (unsigned)n_scenes);
-  const bool aligned = (((uintptr_t)patch_feats | (uintptr_t)queries | (uintptr_t)out_sum) & 15) == 0;
+  const bool aligned = (((uintptr_t)patch_feats | (uintptr_t)out_sum) & 15) == 0;
   cudaStream_t st = dc::as_stream(stream);
-  if (aligned && dim == 768) pixel_fuse_vec_kernel<6><<<grid, kThreads, smem, st>>>(p);       // CLIP ViT-L/14
-  else if (aligned && dim == 512) pixel_fuse_vec_kernel<4><<<grid, kThreads, smem, st>>>(p);  // CLIP ViT-B
-  else if (aligned && dim == 1024) pixel_fuse_vec_kernel<8><<<grid, kThreads, smem, st>>>(p);
-  else pixel_fuse_kernel<<<grid, kThreads, smem, st>>>(p);
+  if (sim_kernel != DC_SIM_NONE) {
+    DC_CHECK_ARG(total_views >= 0 && max_queries_per_scene >= 0, "dc_pixel_fuse: bad extents");
+    const size_t need = dc_pixel_fuse_workspace(total_views, patch_h, patch_w, max_queries_per_scene);
+    DC_CHECK_ARG(workspace && workspace_bytes >= need, "dc_pixel_fuse: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    p.dots = static_cast<float*>(workspace);
+    p.q_stride = query_stride(max_queries_per_scene);
+    if (total_views > 0 && max_queries_per_scene > 0) {
+      const int64_t rows = (int64_t)max_views_per_scene * patch_h * patch_w;
+      dim3 dgrid(blocks_for(rows, n_scenes), (unsigned)n_scenes);
+      patch_query_dots_kernel<<<dgrid, kThreads, 0, st>>>(p);
+      DC_LAUNCH_CHECK();
+    }
+  }
+  if (aligned && (dim == 768 || dim == 512 || dim == 1024)) {  // CLIP ViT-L/14, ViT-B, ViT-H widths
+    const size_t cam_doubles = ((size_t)max_views_per_scene * 12 + 9 + 1) & ~(size_t)1;
+    const size_t tsmem = cam_doubles * sizeof(double) + (size_t)kTilePts * dim * sizeof(float) + kTilePts * sizeof(float);
+    dim3 tgrid((unsigned)dc::ceil_div<int64_t>(max_points_per_scene, kTilePts), (unsigned)n_scenes);
+    static std::once_flag once;
+    static cudaError_t attr_status = cudaSuccess;
+    std::call_once(once, [] {
+      const int cap = 200 * 1024;
+      attr_status = cudaFuncSetAttribute(pixel_fuse_tile_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (attr_status == cudaSuccess) attr_status = cudaFuncSetAttribute(pixel_fuse_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (attr_status == cudaSuccess) attr_status = cudaFuncSetAttribute(pixel_fuse_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    });
+    DC_CHECK_ARG(attr_status == cudaSuccess, "dc_pixel_fuse: cannot raise the shared-memory limit: %s", cudaGetErrorString(attr_status));
+    DC_CHECK_ARG(tsmem <= 200 * 1024, "dc_pixel_fuse: too many views per scene (%d)", max_views_per_scene);
+    if (dim == 768) pixel_fuse_tile_kernel<6><<<tgrid, kThreads, tsmem, st>>>(p);
+    else if (dim == 512) pixel_fuse_tile_kernel<4><<<tgrid, kThreads, tsmem, st>>>(p);
+    else pixel_fuse_tile_kernel<8><<<tgrid, kThreads, tsmem, st>>>(p);
+    if (out_weight) {
+      DC_LAUNCH_CHECK();
+      dim3 zgrid((unsigned)std::min<int64_t>(dc::ceil_div<int64_t>(max_points_per_scene * max_views_per_scene, kThreads * 8), 4096),
+                 (unsigned)n_scenes);
+      zero_invisible_weights_kernel<<<zgrid, kThreads, 0, st>>>(visible, mask_off, out_weight);
+    }
+  }
+  else {
+    pixel_fuse_kernel<<<grid, kThreads, smem, st>>>(p);
+    if (normalize) {
+      DC_LAUNCH_CHECK();
+      DC_CHECK_ARG(sim_kernel == DC_SIM_NONE || out_weight, "dc_pixel_fuse: normalize needs out_weight on this path");
+      pixel_normalize_kernel<<<grid, kThreads, 0, st>>>(out_sum, point_off, view_off, mask_off, visible,
+                                                        sim_kernel != DC_SIM_NONE ? out_weight : nullptr, dim);
+    }
+  }
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
@@ -434,6 +765,24 @@ int dc_pixel_normalize(float* sums, const int64_t* point_off, const int64_t* vie
   if (n_scenes <= 0 || max_points_per_scene <= 0) return DC_OK;
   dim3 grid(blocks_for(max_points_per_scene, n_scenes), (unsigned)n_scenes);
   pixel_normalize_kernel<<<grid, kThreads, 0, dc::as_stream(stream)>>>(sums, point_off, view_off, mask_off, visible, weight, dim);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+int dc_view_clip_gather(const double* points, int64_t n_points, const double* inv_poses, const double* intrinsics,
+                        const float* patch_feats, int n_views, int patch_h, int patch_w, int dim, int height, int width,
+                        float* out, dc_stream_t stream) {
+  DC_CHECK_ARG(points && inv_poses && intrinsics && patch_feats && out, "dc_view_clip_gather: null pointer argument");
+  DC_CHECK_ARG(patch_h > 0 && patch_w > 0 && dim > 0 && height > 0 && width > 0, "dc_view_clip_gather: bad sizes");
+  if (n_points <= 0 || n_views <= 0) return DC_OK;
+  DC_CHECK_ARG(n_views <= 65535, "dc_view_clip_gather: at most 65535 views per call");
+  dim3 grid(blocks_for(n_points, n_views), (unsigned)n_views);
+  const bool vec = dim % 4 == 0 && (((uintptr_t)patch_feats | (uintptr_t)out) & 15) == 0;
+  cudaStream_t st = dc::as_stream(stream);
+  if (vec) view_clip_gather_kernel<true><<<grid, kThreads, 0, st>>>(points, n_points, inv_poses, intrinsics, patch_feats, patch_h,
+                                                                    patch_w, dim, height, width, out);
+  else view_clip_gather_kernel<false><<<grid, kThreads, 0, st>>>(points, n_points, inv_poses, intrinsics, patch_feats, patch_h,
+                                                                  patch_w, dim, height, width, out);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

@@ -613,9 +613,10 @@ class FusionEngine:
         return out
 
     # ------------------------------------------------------------------ pixel-level path
-    def pixel_fuse(self, b: SceneBatch, mask_u8, sim_kernel, norm_feat: bool, spatial_order: bool = True):
+    def pixel_fuse(self, b: SceneBatch, mask_u8, sim_kernel, norm_feat: bool, spatial_order: bool = True, normalize: bool = False):
         """aggregate_features (utils/feature_fusion.py:138-250): returns (sum_features [sum N, C] f32,
-        similarity weights [mask layout] f32 | None). `b.feats` is the (TV, ph, pw, C) patch stack."""
+        similarity weights [mask layout] f32 | None). `b.feats` is the (TV, ph, pw, C) patch stack.
+        `normalize`: return the final features of fuse_points (:266-268) instead of the sums (fused division)."""
         tv, ph, pw, dim = b.feats.shape
         sums = torch.empty((b.total_points, dim), dtype=torch.float32, device=b.device)
         kern = SIM_KERNELS[sim_kernel]
@@ -623,13 +624,17 @@ class FusionEngine:
             if kern != _lib.DC_SIM_NONE else None
         segs = b.segs if kern != _lib.DC_SIM_NONE else None
         perm = self.spatial_sort(b)[0] if spatial_order and b.total_points > 0 else None
+        max_q = max(b.n_queries, default=0) if kern != _lib.DC_SIM_NONE else 0
+        ws_bytes = self.lib.dc_pixel_fuse_workspace(int(tv), int(ph), int(pw), max_q) if kern != _lib.DC_SIM_NONE else 0
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=b.device)
         check(self.lib.dc_pixel_fuse(
             ptr(b.points), ptr(b.off["point"]), ptr(b.off["view"]), ptr(b.inv_poses), ptr(b.intrinsics), ptr(b.off["mask"]),
             ptr(mask_u8), ptr(segs), _lib.torch_dtype_code(segs.dtype) if segs is not None else _lib.DC_I64,
             ptr(b.feats), int(ph), int(pw), int(dim), ptr(b.queries) if kern else None,
             ptr(b.off["query"]) if kern else None, kern, int(bool(norm_feat)), b.n_scenes, max(b.n_points, default=0),
-            max(b.n_views, default=0), b.height, b.width, ptr(perm), ptr(sums), ptr(weight), current_stream()))
-        self.launches += 1
+            max(b.n_views, default=0), b.height, b.width, ptr(perm), ptr(sums), ptr(weight), int(bool(normalize)), int(tv), max_q, ptr(ws), ws_bytes,
+            current_stream()))
+        self.launches += 3 if kern != _lib.DC_SIM_NONE else 1
         return sums, weight
 
     def spatial_sort(self, b: SceneBatch):

@@ -150,7 +150,7 @@ class MultiviewFeatureFusion:
         simw = out["weight"].view(n_views, n_pts) if self.use_similarity else None
         return out["sum"], vis, simw
 
-    def _aggregate(self, eng, points, depths, seg_masks, camera_poses, mv_features, query_embeddings):
+    def _aggregate(self, eng, points, depths, seg_masks, camera_poses, mv_features, query_embeddings, normalize=False):
         segs = [s.cpu().numpy() if isinstance(s, torch.Tensor) else s for s in seg_masks]
         feats = [f.float() for f in mv_features]
         assert feats[0].shape[-1] == self.feature_size
@@ -158,7 +158,7 @@ class MultiviewFeatureFusion:
         b = SceneBatch.from_host([self._scene(points, depths, camera_poses, None, segs, feats, q)], eng.device,
                                  pixel_features=True, staging=self._staging)
         mask, any_vis, _ = eng.visibility(b, self.visibility_threshold, torch.uint8)
-        sums, weight = eng.pixel_fuse(b, mask, self._sim_kernel(), self.norm_feat)
+        sums, weight = eng.pixel_fuse(b, mask, self._sim_kernel(), self.norm_feat, normalize=normalize)
         if self.norm_feat:
             # the reference normalises the caller's upsampled copy, not mv_features itself: nothing to write back
             pass
@@ -167,10 +167,10 @@ class MultiviewFeatureFusion:
     def fuse_points(self, points, colors, labels, depths, seg_masks, camera_poses, mv_features, query_embeddings, device=None):
         device = device or self.device
         eng = self._eng(device)
-        out = self._aggregate(eng, points, depths, seg_masks, camera_poses, mv_features, query_embeddings)
+        # the division by sum_v visibility / sum_v similarity (:266-268) is fused into the fusion kernel
+        out = self._aggregate(eng, points, depths, seg_masks, camera_poses, mv_features, query_embeddings, normalize=True)
         b = out["batch"]
         n_views = len(depths)
-        eng.pixel_normalize(b, out["sum"], out["mask"], out["weight"] if self.use_similarity else None)
         rows = [out["sum"]]
         new_index, kept_off, kept_host, out_off_host, cmask, rows_out = eng.compact(b, out["any"], out["mask"], rows)
         n_kept = int(kept_host[-1])

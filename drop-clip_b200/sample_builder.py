@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import check, current_stream, ptr
 from .engine import FusionEngine, _prefix
 
-__all__ = ["build_samples"]
+__all__ = ["build_samples", "generate_view_clip", "generate_view_clips"]
 
 
 def _dev_tensor(x, dtype, dev):
@@ -122,3 +122,45 @@ def build_samples(samples: Sequence[Dict], view_ids: Sequence[Optional[Sequence[
             "input_features": vfeat[:, dim:], "output_features": vfeat[:, :dim],
             "labels": torch.cat(labels_v) if labels_v else torch.zeros(0, dtype=torch.int64, device=dev),
             "inverse_map": inv, "voxel_off": voff, "points": points}
+
+
+@torch.no_grad()
+def generate_view_clips(pc, world_matrices, K, clip_features, h: int = 480, w: int = 640, device="cuda", return_device: bool = False):
+    """Batched `MVDistilDataset.generate_view_clip` (data/dataset_blender.py:132-171): the per-point CLIP feature of
+    each of V views of one scene. `pc` (N,3) float; `world_matrices` (V,4,4) camera->world as stored in
+    `cameras.<scene>.json` (inverted in fp64 like utils/transforms.py:52-61); `K` (3,3) fp64 (`self.K`);
+    `clip_features` (V, patch_h, patch_w, C) - the rearranged `CLIP.extract` output (:151). File reading and the
+    CLIP tower stay with the caller. Every point is projected (truncation toward zero, z == 0 -> pixel (0,0)),
+    the pixel is clipped into the image (:158-159, no visibility test) and the bicubically upsampled feature of
+    that pixel is returned: (V, N, C) fp32 on the CPU like `.cpu()` (:170) unless `return_device`."""
+    eng = FusionEngine(device)
+    lib, dev = eng.lib, eng.device
+    pts = _dev_tensor(np.asarray(pc) if not isinstance(pc, torch.Tensor) else pc, torch.float64, dev).reshape(-1, 3)
+    poses = np.asarray(world_matrices, dtype=np.float64).reshape(-1, 4, 4)
+    inv = np.ascontiguousarray(np.stack([np.linalg.inv(m) for m in poses]) if len(poses) else poses)
+    feats = clip_features if isinstance(clip_features, torch.Tensor) else torch.from_numpy(np.asarray(clip_features))
+    if feats.dim() == 3:
+        feats = feats.unsqueeze(0)
+    n_views, ph, pw, dim = (int(x) for x in feats.shape)
+    if n_views != len(poses):
+        raise ValueError(f"generate_view_clips: {len(poses)} camera poses for {n_views} feature maps")
+    feats = feats.to(dev, torch.float32).contiguous()
+    d_inv = torch.from_numpy(inv).to(dev)
+    d_K = torch.from_numpy(np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))).to(dev)
+    n = int(pts.shape[0])
+    out = torch.empty((n_views, n, dim), dtype=torch.float32, device=dev)
+    if n and n_views:
+        check(lib.dc_view_clip_gather(ptr(pts), n, ptr(d_inv), ptr(d_K), ptr(feats), n_views, ph, pw, dim, int(h), int(w),
+                                      ptr(out), current_stream()))
+    if return_device:
+        return out
+    host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+    host.copy_(out, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return host
+
+
+def generate_view_clip(pc, world_matrix, K, clip_feature, h: int = 480, w: int = 640, device="cuda"):
+    """One view: (N, C) fp32 CPU tensor, the return value of the reference method (data/dataset_blender.py:132-171)."""
+    feat = clip_feature if isinstance(clip_feature, torch.Tensor) else torch.from_numpy(np.asarray(clip_feature))
+    return generate_view_clips(pc, np.asarray(world_matrix, dtype=np.float64)[None], K, feat[None], h, w, device)[0]

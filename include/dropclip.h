@@ -225,13 +225,30 @@ DC_API int dc_compact_mask(const void* mask, int elem_size, const int64_t* mask_
  *   out_weight  [mask layout] fp32 similarity weights (similarity_mask :238) or NULL
  *   perm        [total_points] from dc_spatial_sort or NULL: processing order of the points inside a scene
  *               (neighbouring warps then share bicubic taps in L1); results do not depend on it
+ *   normalize   1: out_sum holds the final features of fuse_points :266-268 (sums divided by sum_v weight, or by the
+ *               number of views that see the point without similarity) - saves the separate dc_pixel_normalize pass
+ *   workspace   dc_pixel_fuse_workspace(...) bytes (sim_kernel != NONE): the similarity of an interpolated feature
+ *               with a query is linear in the 16 taps, so patch-cell . query dots are computed once per view and
+ *               interpolated with the same bicubic weights (then divided by |f| under norm_feat)
  */
 DC_API int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t* view_off,
                   const float* inv_poses, const double* intrinsics, const int64_t* mask_off,
                   const uint8_t* visible, const void* seg, int seg_dtype, const float* patch_feats, int patch_h,
                   int patch_w, int dim, const float* queries, const int64_t* query_off, int sim_kernel,
                   int norm_feat, int n_scenes, int64_t max_points_per_scene, int max_views_per_scene,
-                  int height, int width, const int64_t* perm, float* out_sum, float* out_weight, dc_stream_t stream);
+                  int height, int width, const int64_t* perm, float* out_sum, float* out_weight, int normalize,
+                  int64_t total_views, int max_queries_per_scene, void* workspace, size_t workspace_bytes,
+                  dc_stream_t stream);
+/* workspace of dc_pixel_fuse when sim_kernel != NONE: the per-view (patch cell x query) dot table (0 bytes otherwise) */
+DC_API size_t dc_pixel_fuse_workspace(int64_t total_views, int patch_h, int patch_w, int max_queries_per_scene);
+/* generate_view_clip (data/dataset_blender.py:132-171): out[v, i, :] = bicubic(patch_feats[v])[clip(pixel of point i in view v)].
+ * Projection in fp64 with the json world_matrix inverted in fp64 by the caller (utils/transforms.py:52-61), y/z flip,
+ * truncation toward zero, pixel (0,0) when the projected z is 0, coordinates clipped into the image (:158-159); no
+ * visibility test. inv_poses [n_views,16] fp64, intrinsics [9] fp64 (self.K), patch_feats [n_views, ph, pw, dim] fp32,
+ * out [n_views, n_points, dim] fp32. */
+DC_API int dc_view_clip_gather(const double* points, int64_t n_points, const double* inv_poses, const double* intrinsics,
+                        const float* patch_feats, int n_views, int patch_h, int patch_w, int dim, int height, int width,
+                        float* out, dc_stream_t stream);
 /* feat[j,:] = sum[j,:] / denom[j] with denom = sum_v weight (similarity) or sum_v visible. */
 DC_API int dc_pixel_normalize(float* sums, const int64_t* point_off, const int64_t* view_off, const int64_t* mask_off,
                        const uint8_t* visible, const float* weight, int n_scenes, int64_t max_points_per_scene,

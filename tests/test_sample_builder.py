@@ -76,3 +76,67 @@ def test_build_samples_errors_like_numpy():
     bad["label"][:] = 50                                       # no such per_obj row
     with pytest.raises(IndexError):
         build_samples([bad], [None], [np.arange(10)], 0.3)
+
+
+# ---- generate_view_clip (data/dataset_blender.py:132-171), pinned by outputs of the unmodified reference method ----
+VIEW_CLIP_CASES = ["scene", "wild", "small_odd_dim", "downsample"]
+
+
+def _view_clip_case(name):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "view_clip.npz"))
+    h, w = (int(x) for x in g[f"{name}_hw"])
+    return g[f"{name}_pc"], g[f"{name}_world_matrix"], g[f"{name}_K"], torch.from_numpy(g[f"{name}_patch"]), h, w, g[f"{name}_out"]
+
+
+@pytest.mark.parametrize("name", VIEW_CLIP_CASES)
+def test_oracle_view_clip_vs_reference_golden(name):
+    from oracle import sample_ref
+    pc, wm, K, patch, h, w, want = _view_clip_case(name)
+    got, pix = sample_ref.view_clip_ref(pc, wm, K, patch, h, w)
+    assert got.dtype == torch.float32 and got.shape == want.shape
+    np.testing.assert_array_equal(got.numpy(), want)  # same numpy/torch calls on the same machine: identical
+    assert pix[:, 0].min() >= 0 and pix[:, 0].max() <= w - 1 and pix[:, 1].min() >= 0 and pix[:, 1].max() <= h - 1
+    if name == "wild":
+        assert (pix[:13] == 0).all()  # camera-plane points keep pixel (0,0); non-finite quotients clip to 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", VIEW_CLIP_CASES)
+def test_generate_view_clip_vs_reference_golden(name):
+    from dropclip_b200.sample_builder import generate_view_clip
+    pc, wm, K, patch, h, w, want = _view_clip_case(name)
+    got = generate_view_clip(pc, wm, K, patch, h, w)
+    assert got.dtype == torch.float32 and tuple(got.shape) == want.shape and got.device.type == "cpu"
+    # bicubic taps in fp32 in a different summation order than ATen: 1e-3 relative to the feature scale
+    np.testing.assert_allclose(got.numpy(), want, rtol=1e-3, atol=1e-3 * float(np.abs(want).max()))
+    # every point must have landed on the same pixel: a wrong pixel shows up as an O(1) row difference
+    row_err = np.abs(got.numpy() - want).max(1)
+    assert row_err.max() < 5e-3 * float(np.abs(want).max())
+
+
+@pytest.mark.gpu
+def test_generate_view_clips_batch_equals_single_views_and_oracle():
+    from oracle import sample_ref
+    from dropclip_b200.sample_builder import generate_view_clip, generate_view_clips
+    rng = np.random.default_rng(5)
+    pc = rng.uniform(-3, 3, size=(1500, 3))
+    K = np.array([[100.0, 0, 63.5], [0, 100.0, 47.5], [0, 0, 1]])
+    poses = []
+    for i in range(5):
+        a = 2 * np.pi * i / 5
+        m = np.eye(4)
+        m[:3, 3] = [8 * np.cos(a), 8 * np.sin(a), 5.0]
+        c, s = np.cos(a), np.sin(a)
+        m[:3, :3] = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]]) @ np.array([[0, 0, 1.0], [1.0, 0, 0], [0, 1.0, 0]])
+        poses.append(m)
+    patch = torch.from_numpy(rng.standard_normal((5, 12, 16, 64)).astype(np.float32))
+    batch = generate_view_clips(pc, np.stack(poses), K, patch, 96, 128)
+    assert tuple(batch.shape) == (5, 1500, 64)
+    for v in range(5):
+        single = generate_view_clip(pc, poses[v], K, patch[v], 96, 128)
+        assert torch.equal(single, batch[v])
+        want, _ = sample_ref.view_clip_ref(pc, poses[v], K, patch[v], 96, 128)
+        np.testing.assert_allclose(batch[v].numpy(), want.numpy(), rtol=1e-3, atol=1e-3 * float(want.abs().max()))
+    empty = generate_view_clips(np.zeros((0, 3)), np.stack(poses), K, patch, 96, 128)
+    assert tuple(empty.shape) == (5, 0, 64)
