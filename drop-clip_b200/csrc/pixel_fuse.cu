@@ -6,8 +6,9 @@
 // whole map with the query matrix, builds a per-pixel similarity metric, and finally gathers the
 // visible projected pixels. Only those gathered pixels matter, so this kernel evaluates the 16
 // bicubic taps directly at each visible (point, view), in registers, and never materialises the
-// map. It is point-major: a warp owns a point, walks its views in order (same accumulation
-// order as `sum_features[mask] += feat3d`), and writes the point's row once.
+// map. Rows are accumulated over the views in view order (same order as `sum_features[mask] += feat3d`)
+// and written once. The query similarity of an interpolated feature comes from a per-view table of
+// (patch cell . query) dots interpolated with the same weights (patch_query_dots_kernel).
 //
 // Bicubic weights follow ATen's upsample_bicubic2d (align_corners=False, A=-0.75, source index
 // scale*(dst+0.5)-0.5 un-clamped, taps clamped to the border).
@@ -150,6 +151,17 @@ __device__ __forceinline__ float finish_weight(const PixParams& p, float first, 
   return weight;
 }
 
+// seg_at in two halves: the load (requested early) and the range check / narrowing (done where the id is needed), so
+// that the scoreboard wait for this cold, scattered load sits behind the tap arithmetic.
+__device__ __forceinline__ long long seg_raw(const void* seg, int dtype, int64_t idx) {
+  long long v;
+  if (dtype == DC_U8) v = (long long)__ldg(reinterpret_cast<const uint8_t*>(seg) + idx);
+  else if (dtype == DC_I32) v = (long long)__ldg(reinterpret_cast<const int32_t*>(seg) + idx);
+  else v = __ldg(reinterpret_cast<const long long*>(seg) + idx);
+  return v;
+}
+__device__ __forceinline__ int seg_id(long long v) { return (v < 0 || v > 0x7fffffff) ? -1 : (int)v; }
+
 __global__ void __launch_bounds__(kThreads) pixel_fuse_kernel(PixParams p) {
   extern __shared__ double s_cam[];  // [n_views][12] + [9]
   const int scene = blockIdx.y;
@@ -262,138 +274,13 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_kernel(PixParams p) {
   }
 }
 
-// Same arithmetic with 128-bit accesses: a lane owns 4 consecutive channels of every 128-channel chunk
-// (dim = 128 * kChunks; CLIP ViT-L/14: 6 chunks), which cuts the load instructions per visible
-// (point, view) from 16 * dim / 32 to 16 * dim / 128. The query similarities come from the per-view dot table
-// (pixel_weight), so the kernel reads 49 KB of taps per pair and no queries (the first version read the Q x C query
-// matrix per pair as well: 114 KB of L1 traffic and 16 k extra FMA per pair, ncu: L1 data pipe 58 %, long-scoreboard 4.9/issue).
-template <int kChunks>
-__global__ void __launch_bounds__(kThreads, 2) pixel_fuse_vec_kernel(PixParams p) {
-  extern __shared__ double s_cam[];  // [n_views][12] + [9]
-  const int scene = blockIdx.y;
-  const int64_t p0 = p.point_off[scene];
-  const int64_t n_pts = p.point_off[scene + 1] - p0;
-  const int64_t v0 = p.view_off[scene];
-  const int n_views = (int)(p.view_off[scene + 1] - v0);
-  for (int i = threadIdx.x; i < n_views * 12; i += kThreads) {
-    const int v = i / 12, e = i - v * 12;
-    s_cam[i] = (double)__ldg(p.inv_poses + (v0 + v) * 16 + e);
-  }
-  double* s_K = s_cam + n_views * 12;
-  if (threadIdx.x < 9) s_K[threadIdx.x] = __ldg(p.intrinsics + (int64_t)scene * 9 + threadIdx.x);
-  __syncthreads();
-
-  constexpr int kDim = 128 * kChunks;
-  const int lane = threadIdx.x & 31;
-  const int n_q = p.sim_kernel != DC_SIM_NONE ? (int)(p.query_off[scene + 1] - p.query_off[scene]) : 0;
-  const float scale_y = (float)p.ph / (float)p.height, scale_x = (float)p.pw / (float)p.width;
-  const int64_t hw = (int64_t)p.height * p.width;
-  const uint8_t* vis_scene = p.visible + p.mask_off[scene];
-  float* w_scene = p.out_weight ? p.out_weight + p.mask_off[scene] : nullptr;
-
-  for (int64_t s_pos = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); s_pos < n_pts; s_pos += (int64_t)gridDim.x * kWarps) {
-    const int64_t i = p.perm ? __ldg(p.perm + p0 + s_pos) : s_pos;  // spatially sorted processing order, original indexing
-    const double x = __ldg(p.points + 3 * (p0 + i)), y = __ldg(p.points + 3 * (p0 + i) + 1),
-                 z = __ldg(p.points + 3 * (p0 + i) + 2);
-    float4 acc[kChunks];
-#pragma unroll
-    for (int k = 0; k < kChunks; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int v = 0; v < n_views; ++v) {
-      const bool vis = vis_scene[(int64_t)v * n_pts + i] != 0;  // warp-uniform
-      if (!vis) {
-        if (w_scene && lane == 0) w_scene[(int64_t)v * n_pts + i] = 0.f;
-        continue;
-      }
-      const double* m = s_cam + v * 12;
-      double cx = __dadd_rn(m[3], __fma_rn(m[2], z, __fma_rn(m[1], y, __dmul_rn(m[0], x))));
-      double cy = __dadd_rn(m[7], __fma_rn(m[6], z, __fma_rn(m[5], y, __dmul_rn(m[4], x))));
-      double cz = __dadd_rn(m[11], __fma_rn(m[10], z, __fma_rn(m[9], y, __dmul_rn(m[8], x))));
-      cy = -cy;
-      cz = -cz;
-      const double qx = __fma_rn(s_K[2], cz, __fma_rn(s_K[1], cy, __dmul_rn(s_K[0], cx)));
-      const double qy = __fma_rn(s_K[5], cz, __fma_rn(s_K[4], cy, __dmul_rn(s_K[3], cx)));
-      const double qz = __fma_rn(s_K[8], cz, __fma_rn(s_K[7], cy, __dmul_rn(s_K[6], cx)));
-      int pu = 0, pv = 0;
-      if (qz != 0.0) {
-        pu = (int)__ddiv_rn(qx, qz);
-        pv = (int)__ddiv_rn(qy, qz);
-      }
-      int iy[4], ix[4];
-      float wy[4], wx[4];
-      cubic_taps(pv, scale_y, p.ph, iy, wy);
-      cubic_taps(pu, scale_x, p.pw, ix, wx);
-      const float4* pm = reinterpret_cast<const float4*>(p.patch + (v0 + v) * (int64_t)p.ph * p.pw * kDim);
-      const float* dots_view = p.dots + (v0 + v) * (int64_t)p.ph * p.pw * p.q_stride;
-      const float first_dot = p.sim_kernel != DC_SIM_NONE ? interp_dot(p, dots_view, iy, ix, wy, wx, lane, n_q) : 0.f;
-      float4 f[kChunks];
-#pragma unroll
-      for (int k = 0; k < kChunks; ++k) f[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      // ATen order: interpolate along x inside each of the 4 rows, then along y
-#pragma unroll
-      for (int ty = 0; ty < 4; ++ty) {
-        const float4* row = pm + (int64_t)iy[ty] * p.pw * (kDim / 4);
-        const float4* t0 = row + (int64_t)ix[0] * (kDim / 4) + lane;
-        const float4* t1 = row + (int64_t)ix[1] * (kDim / 4) + lane;
-        const float4* t2 = row + (int64_t)ix[2] * (kDim / 4) + lane;
-        const float4* t3 = row + (int64_t)ix[3] * (kDim / 4) + lane;
-#pragma unroll
-        for (int k = 0; k < kChunks; ++k) {
-          const float4 a = __ldg(t0 + k * 32), b = __ldg(t1 + k * 32), c = __ldg(t2 + k * 32), d = __ldg(t3 + k * 32);
-          f[k].x = fmaf(a.x * wx[0] + b.x * wx[1] + c.x * wx[2] + d.x * wx[3], wy[ty], f[k].x);
-          f[k].y = fmaf(a.y * wx[0] + b.y * wx[1] + c.y * wx[2] + d.y * wx[3], wy[ty], f[k].y);
-          f[k].z = fmaf(a.z * wx[0] + b.z * wx[1] + c.z * wx[2] + d.z * wx[3], wy[ty], f[k].z);
-          f[k].w = fmaf(a.w * wx[0] + b.w * wx[1] + c.w * wx[2] + d.w * wx[3], wy[ty], f[k].w);
-        }
-      }
-      float nrm = 1.f;
-      if (p.norm_feat) {
-        float ss = 0.f;
-#pragma unroll
-        for (int k = 0; k < kChunks; ++k) ss = fmaf(f[k].x, f[k].x, fmaf(f[k].y, f[k].y, fmaf(f[k].z, f[k].z, fmaf(f[k].w, f[k].w, ss))));
-        nrm = sqrtf(dc::warp_sum(ss));
-#pragma unroll
-        for (int k = 0; k < kChunks; ++k) {
-          f[k].x = f[k].x / nrm;
-          f[k].y = f[k].y / nrm;
-          f[k].z = f[k].z / nrm;
-          f[k].w = f[k].w / nrm;
-        }
-      }
-      float weight = 1.f;
-      if (p.sim_kernel != DC_SIM_NONE) {
-        const int id = seg_at(p.seg, p.seg_dtype, (v0 + v) * hw + (int64_t)pv * p.width + pu);
-        weight = 0.f;  // pixels whose id has no query keep metric 0 (quirk q13)
-        if (id >= 0 && id < n_q)
-          weight = finish_weight(p, first_dot, nrm, id, n_q, lane, [&](int o) { return interp_dot(p, dots_view, iy, ix, wy, wx, o, n_q); });
-        if (w_scene && lane == 0) w_scene[(int64_t)v * n_pts + i] = weight;
-#pragma unroll
-        for (int k = 0; k < kChunks; ++k) {  // feat2d[ys,xs] * metric, then +=  (two roundings)
-          acc[k].x += f[k].x * weight;
-          acc[k].y += f[k].y * weight;
-          acc[k].z += f[k].z * weight;
-          acc[k].w += f[k].w * weight;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < kChunks; ++k) {
-          acc[k].x += f[k].x;
-          acc[k].y += f[k].y;
-          acc[k].z += f[k].z;
-          acc[k].w += f[k].w;
-        }
-      }
-    }
-    float4* dst = reinterpret_cast<float4*>(p.out_sum + (p0 + i) * kDim) + lane;
-#pragma unroll
-    for (int k = 0; k < kChunks; ++k) dst[k * 32] = acc[k];
-  }
-}
-
-// Tile variant of the 128-bit kernel: a CTA owns kTilePts consecutive points of the (Morton-sorted) processing
+// The fast path (dim = 128 * kChunks: CLIP widths 512 / 768 / 1024). A lane owns 4 consecutive channels of every
+// 128-channel chunk (128-bit tap loads). A CTA owns kTilePts consecutive points of the (Morton-sorted) processing
 // order and walks the views IN STEP (one barrier per view that sees any of them). Neighbouring points project into
 // the same patch cells of a view, so while the CTA is on view v its warps keep hitting the same ~50 KB of taps in
-// L1. The point-major kernel above lets every warp drift through the views at its own pace: the ncu capture of
-// round 1 showed 43 % L1 hits, 10 GB of L2 reads per 8-view scene and 6.6 long-scoreboard stall cycles per issue.
+// L1. A point-major version (one warp per point, all its views) let every warp drift through the views at its own
+// pace: its ncu capture showed 43 % L1 hits, 10 GB of L2 reads per 8-view scene and 6.6 long-scoreboard stall cycles
+// per issue; this kernel: 79 % L1 hits, 3.4 GB, 4.0 (profiles/r01_pixel_fuse.md).
 // The per-point accumulators live in shared memory (kTilePts x dim fp32) so that the visible points of a view can
 // be dealt to the warps round-robin whatever their position in the tile; a point is touched by one warp per view
 // and the barrier orders the views, so every row is accumulated in view order exactly like `sum_features[mask] +=`.
@@ -468,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 2) pixel_fuse_tile_kernel(PixParams 
       cubic_taps(pu, scale_x, p.pw, ix, wx);
       // the instance id and the first round of query dots are requested before the taps: both are cold loads whose
       // latency then hides behind the 96 tap loads instead of sitting in front of the accumulator update
-      const int id = p.sim_kernel != DC_SIM_NONE ? seg_at(p.seg, p.seg_dtype, (v0 + v) * hw + (int64_t)pv * p.width + pu) : -1;
+      long long raw_id = p.sim_kernel != DC_SIM_NONE ? seg_raw(p.seg, p.seg_dtype, (v0 + v) * hw + (int64_t)pv * p.width + pu) : -1;
       const float first_dot = p.sim_kernel != DC_SIM_NONE ? interp_dot(p, dots_view, iy, ix, wy, wx, lane, n_q) : 0.f;
       // Chunk-major: the 16 taps of one 128-channel chunk are requested back to back (16 independent 128-bit loads
       // in flight per lane) and folded in the ATen order (along x inside each row, then along y); finished chunks
@@ -516,6 +403,8 @@ __global__ void __launch_bounds__(kThreads, 2) pixel_fuse_tile_kernel(PixParams 
       }
       float4* acc = s_acc + slot * (kDim / 4) + lane;
       if (p.sim_kernel != DC_SIM_NONE) {
+        asm volatile("" : "+l"(raw_id));  // keeps the narrowing (and the wait for the load) down here
+        const int id = seg_id(raw_id);
         float weight = 0.f;  // pixels whose id has no query keep metric 0 (quirk q13)
         if (id >= 0 && id < n_q)
           weight = finish_weight(p, first_dot, nrm, id, n_q, lane, [&](int o) { return interp_dot(p, dots_view, iy, ix, wy, wx, o, n_q); });
