@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--e2e-scenes", type=int, default=4, help="scenes per e2e step through the host API")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the supplementary configs 4/5 (pixel-level fusion, grounding)")
     return ap.parse_args()
 
 
@@ -364,6 +365,14 @@ def run_ours(args):
                       "tools/preprocess_data.py:268", "steps": n_e2e, "pipelined": e2e_pipelined}
         del host, M
 
+    # ---- BASELINE configs 4 and 5 (supplementary; rank 0, N=1)
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            extras = other_configs(dev, eng)
+        except Exception as exc:  # never let a supplementary measurement break the contract line
+            extras = {"error": repr(exc)}
+
     # ---- CPU baseline (rank 0, N=1): one scene of the workload through the oracle port
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -387,11 +396,71 @@ def run_ours(args):
                        "parallelism": "scene-parallel x%d, no data-path collective; all_gather of fused features" % world,
                        "l2": "inputs per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % resident_gb},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "resident_uint8_instance_maps": alt,
+            "resident_uint8_instance_maps": alt, "other_configs": extras,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(dev, eng):
+    """BASELINE.json configs 4 and 5 on one GPU, as supplementary numbers next to the headline (CUDA events, median of 5
+    after 3 warm-ups): pixel-level fusion of one scene (use_obj_prior=0, V=8, sim kernel max, norm_feat) and 3D grounding
+    of 200 k points x 256 prompts (fp16, paired softmax, in-place normalisation + GEMM + min-max threshold)."""
+    from dropclip_b200.engine import batch_from_device
+    from dropclip_b200.scenes import make_scene
+    out = {}
+
+    def median_ms(fn, reps=5, warm=3):
+        ts = []
+        for it in range(warm + reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            if it >= warm:
+                ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2]
+
+    sc = make_scene(1234, n_views=8, n_points=100_000, n_objects=21, device=str(dev), as_torch=True, pixel_features=True,
+                    feature_dtype=torch.float32)
+    patches = torch.stack(sc["mv_features"]).contiguous()
+    sc_obj = dict(sc)
+    sc_obj["mv_features"] = [torch.zeros((1, 768), device=dev, dtype=torch.float16) for _ in range(8)]
+    b = batch_from_device([sc_obj], dev)
+    b.feats = patches
+    mask, _, _ = eng.visibility(b, 0.05, torch.uint8)
+    ms = median_ms(lambda: eng.pixel_fuse(b, mask, "max", True, normalize=True))
+    pairs = int(mask.sum().item())
+    out["pixel_level_fusion"] = {"workload": "configs[3]: 1 scene, V=8, N=100k, C=768, Q=21, 24x32 patch maps, sim max, norm_feat",
+                                 "ms_per_scene": ms, "visible_point_views": pairs,
+                                 "tap_tflops": 2.0 * 16 * 768 * pairs / (ms * 1e-3) / 1e12}
+    del b, mask, patches, sc, sc_obj
+
+    from dropclip_b200 import _lib as lib_mod
+    n, p, c = 200_000, 256, 768
+    g = torch.Generator(device=dev).manual_seed(0)
+    x0 = torch.randn((n, c), generator=g, device=dev).half()
+    t = torch.randn((p, c), generator=g, device=dev)
+    t = (t / t.norm(dim=-1, keepdim=True)).half()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ts = []
+    for it in range(8):
+        x = x0.clone()
+        flush.zero_()  # 256 MB > L2: the features come from HBM
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        vals, pred, mm = eng.ground(x, t, lib_mod.DC_GROUND_PAIRED, 0.1, normalize=True)
+        eng.minmax_threshold(vals.view(-1), mm, False, 0.7, True)
+        e.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            ts.append(a.elapsed_time(e))
+    ms = sorted(ts)[len(ts) // 2]
+    out["grounding"] = {"workload": "configs[4]: 200k points x 256 prompts x 768, fp16, paired softmax, predict()",
+                        "ms": ms, "points_per_s": n / (ms * 1e-3), "useful_tflops": 2.0 * n * p * c / (ms * 1e-3) / 1e12}
+    return out
 
 
 def main():
