@@ -13,7 +13,6 @@
 // Bicubic weights follow ATen's upsample_bicubic2d (align_corners=False, A=-0.75, source index
 // scale*(dst+0.5)-0.5 un-clamped, taps clamped to the border).
 #include <algorithm>
-#include <mutex>
 
 #include "common.cuh"
 
@@ -624,16 +623,11 @@ int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t*
     const size_t cam_doubles = ((size_t)max_views_per_scene * 12 + 9 + 1) & ~(size_t)1;
     const size_t tsmem = cam_doubles * sizeof(double) + (size_t)kTilePts * dim * sizeof(float) + kTilePts * sizeof(float);
     dim3 tgrid((unsigned)dc::ceil_div<int64_t>(max_points_per_scene, kTilePts), (unsigned)n_scenes);
-    static std::once_flag once;
-    static cudaError_t attr_status = cudaSuccess;
-    std::call_once(once, [] {
-      const int cap = 200 * 1024;
-      attr_status = cudaFuncSetAttribute(pixel_fuse_tile_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-      if (attr_status == cudaSuccess) attr_status = cudaFuncSetAttribute(pixel_fuse_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-      if (attr_status == cudaSuccess) attr_status = cudaFuncSetAttribute(pixel_fuse_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    });
-    DC_CHECK_ARG(attr_status == cudaSuccess, "dc_pixel_fuse: cannot raise the shared-memory limit: %s", cudaGetErrorString(attr_status));
     DC_CHECK_ARG(tsmem <= 200 * 1024, "dc_pixel_fuse: too many views per scene (%d)", max_views_per_scene);
+    // the attribute belongs to the (function, device) pair, so it is set on every call for the device in use
+    const void* fn = dim == 768 ? (const void*)pixel_fuse_tile_kernel<6>
+                   : dim == 512 ? (const void*)pixel_fuse_tile_kernel<4> : (const void*)pixel_fuse_tile_kernel<8>;
+    DC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (dim == 768) pixel_fuse_tile_kernel<6><<<tgrid, kThreads, tsmem, st>>>(p);
     else if (dim == 512) pixel_fuse_tile_kernel<4><<<tgrid, kThreads, tsmem, st>>>(p);
     else pixel_fuse_tile_kernel<8><<<tgrid, kThreads, tsmem, st>>>(p);
