@@ -174,9 +174,12 @@ extern "C" int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_vi
   cudaStream_t st = dc::as_stream(stream);
   DC_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (size_t)total_views * nbins, st));
   DC_CUDA(cudaMemsetAsync(outside, 0, sizeof(uint32_t) * (size_t)total_views, st));
-  // enough CTAs per view to fill the machine a few times over, never fewer than one
+  // CTAs of ~512 KB: enough of them per view to fill the machine a few times over when there are few views, and small
+  // enough that the last wave does not leave SMs idle when there are many (4672 views of 2.4 MB: one CTA per view
+  // ran at 6.9 TB/s, four at 7.3 TB/s)
   const int64_t vec_per_view = pixels_per_view * esize / 16;
   int64_t want = dc::ceil_div<int64_t>((int64_t)dc::sm_count() * 8, total_views);
+  want = max(want, pixels_per_view * esize / (512 << 10));
   int64_t cap = dc::ceil_div<int64_t>(vec_per_view, (int64_t)kThreads * 4);
   unsigned gx = (unsigned)max((int64_t)1, min(want, max((int64_t)1, cap)));
   dim3 grid(gx, (unsigned)total_views);
