@@ -29,7 +29,8 @@ SIGNATURES = {
     "dc_project_visibility_sorted": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int64, c_int, c_int, c_int, c_double, P, P, P,
                                              P, c_size_t, P]),
     "dc_unpack_visibility": (c_int, [P, P, P, P, P, c_int, c_int64, c_int64, P, c_int, P]),
-    "dc_unpack_visibility_compact": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int64, c_int64, P, c_int, P]),
+    "dc_unpack_visibility_compact": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int64, c_int64, P, c_int, P, c_size_t, P]),
+    "dc_unpack_compact_workspace": (c_size_t, [c_int64, c_int]),
     "dc_seg_histogram": (c_int, [P, c_int, c_int64, c_int64, c_int, P, P, P]),
     "dc_view_table": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, P, P, P, P]),
     "dc_view_score_ld": (c_int, [c_int]),

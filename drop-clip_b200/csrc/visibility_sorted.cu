@@ -628,6 +628,126 @@ __global__ void __launch_bounds__(kThreads) unpack_kernel(const uint32_t* __rest
 
 
 
+// ---- wide uint8 unpack of the compacted masks -------------------------------------------------------------------
+// The thread-per-point kernel above writes one byte per (point, view): 32-byte warp stores, ~5 instructions per byte,
+// L2 write transactions at 70 % (ncu). Here a thread owns FOUR consecutive output columns of a scene: the same byte
+// of their four record words is gathered into one register (PRMT), one shift + mask then yields the four mask bytes
+// of a view as a 32-bit word, and a warp writes 124 contiguous bytes per view with 4-byte stores. Rows of the
+// compacted mask start at arbitrary byte addresses (stride = number of kept points), so the word a thread stores is
+// funnel-shifted together from its own columns and its right neighbour's (lane 31 of a warp repeats lane 0 of the
+// next warp and stores nothing); the few bytes in front of the first aligned word and at the end of a row are
+// written one by one.
+__global__ void __launch_bounds__(kThreads) kept_positions_kernel(const int64_t* __restrict__ rank, const int64_t* __restrict__ point_off,
+                                                                  const uint8_t* __restrict__ any_visible,
+                                                                  const int64_t* __restrict__ new_index, uint32_t* __restrict__ src_pos) {
+  const int scene = blockIdx.y;
+  const int64_t p0 = point_off[scene], n = point_off[scene + 1] - p0;
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n || !any_visible[p0 + i]) return;
+  src_pos[new_index[p0 + i]] = (uint32_t)(p0 + rank[p0 + i]);  // sorted position of the point behind output column new_index
+}
+
+__global__ void __launch_bounds__(kThreads) unpack_compact_wide_kernel(const uint32_t* __restrict__ records,
+                                                                       const uint32_t* __restrict__ src_pos,
+                                                                       const int64_t* __restrict__ view_off,
+                                                                       const int64_t* __restrict__ kept_off,
+                                                                       const int64_t* __restrict__ out_off, int64_t total_points,
+                                                                       uint8_t* __restrict__ out) {
+  const int scene = blockIdx.y;
+  const int64_t kept0 = kept_off[scene];
+  const int64_t n_kept = kept_off[scene + 1] - kept0;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int64_t g = warp * 31 + lane;  // group of four columns; lane 31 repeats lane 0 of the next warp
+  if (warp * 31 * 4 >= n_kept) return;  // whole warp beyond the scene
+  const int n_v = (int)(view_off[scene + 1] - view_off[scene]);
+  const int64_t c0 = 4 * g;
+  int64_t pos[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) pos[k] = (c0 + k < n_kept) ? (int64_t)__ldg(src_pos + kept0 + c0 + k) : -1;
+  uint8_t* base = out + out_off[scene];
+  // Interior warps (every column of the warp and of its right neighbour group exists, and the warp does not hold the
+  // row start) run a lean loop: no per-byte code, the address and the funnel shift advance by additions only.
+  if (warp > 0 && (warp * 31 + 32) * 4 <= n_kept) {
+    uint8_t* ptr = base + c0;                    // my first column in row v (advanced by n_kept per view)
+    unsigned low = (unsigned)(uintptr_t)ptr;     // its low address bits: they alone decide the alignment
+    const unsigned step = (unsigned)n_kept;
+    // one view: my four bytes, my right neighbour's, and the aligned word they form at or after my first column
+    // (byte shift by PRMT: selector 0x3210 + 0x1111 * off takes my bytes off..3 and the neighbour's bytes 0..off-1)
+    auto emit = [&](uint32_t mine) {
+      const uint32_t next = __shfl_down_sync(0xffffffffu, mine, 1);
+      const unsigned off = (0u - low) & 3u;
+      const uint32_t word = __byte_perm(mine, next, 0x3210u + 0x1111u * off);
+      if (lane < 31) *reinterpret_cast<uint32_t*>(ptr + off) = word;
+      ptr += n_kept;
+      low += step;
+    };
+    for (int w = 0; w * 32 < n_v; ++w) {
+      uint32_t r[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r[k] = __ldg(records + (int64_t)w * total_points + pos[k]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int left = n_v - (w * 32 + j * 8);  // views left in this byte (warp-uniform)
+        if (left <= 0) break;
+        const uint32_t lo2 = __byte_perm(r[0], r[1], 0x0040 + j * 0x11);
+        const uint32_t hi2 = __byte_perm(r[2], r[3], 0x0040 + j * 0x11);
+        const uint32_t packed = __byte_perm(lo2, hi2, 0x5410);
+        if (left >= 8) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) emit((packed >> i) & 0x01010101u);
+        } else {
+          for (int i = 0; i < left; ++i) emit((packed >> i) & 0x01010101u);
+        }
+      }
+    }
+    return;
+  }
+  for (int w = 0; w * 32 < n_v; ++w) {
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = pos[k] >= 0 ? __ldg(records + (int64_t)w * total_points + pos[k]) : 0u;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      if (w * 32 + j * 8 >= n_v) break;  // warp-uniform
+      // byte j of the four records side by side: bits i of the four bytes are view 32 w + 8 j + i of the four columns
+      const uint32_t lo2 = __byte_perm(r[0], r[1], 0x0040 + j * 0x11);  // (r0.byte j, r1.byte j, -, -)
+      const uint32_t hi2 = __byte_perm(r[2], r[3], 0x0040 + j * 0x11);
+      const uint32_t packed = __byte_perm(lo2, hi2, 0x5410);
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i) {
+        const int v = w * 32 + j * 8 + i;
+        if (v >= n_v) break;  // warp-uniform
+        const uint32_t mine = (packed >> i) & 0x01010101u;
+        const uint32_t next = __shfl_down_sync(0xffffffffu, mine, 1);
+        uint8_t* row = base + (int64_t)v * n_kept;
+        const int m = (int)((uintptr_t)row & 3);  // misalignment of the row start (warp-uniform)
+        if (m == 0) {
+          if (lane < 31) {
+            if (c0 + 3 < n_kept) *reinterpret_cast<uint32_t*>(row + c0) = mine;
+            else
+              for (int k = 0; k < 4; ++k)
+                if (c0 + k < n_kept) row[c0 + k] = (uint8_t)(mine >> (8 * k));
+          }
+        } else {
+          // aligned word holding columns c0 + 4 - m .. c0 + 7 - m: my last m bytes below my neighbour's first 4 - m
+          const uint32_t word = __funnelshift_r(mine, next, 8 * (4 - m));
+          const int64_t first = c0 + 4 - m;
+          if (lane < 31) {
+            if (first + 3 < n_kept) *reinterpret_cast<uint32_t*>(row + first) = word;
+            else
+              for (int k = 0; k < 4; ++k)
+                if (first + k < n_kept) row[first + k] = (uint8_t)(word >> (8 * k));
+          }
+          if (g == 0)  // the bytes in front of the first aligned word
+            for (int k = 0; k < 4 - m; ++k)
+              if (k < n_kept) row[k] = (uint8_t)(mine >> (8 * k));
+        }
+      }
+    }
+  }
+}
+
 // Serialises the users of c_views on one device: holds a process-wide mutex while work is enqueued, makes the
 // caller's stream wait for the previous user's last kernel, and records the new "last use" event on release.
 struct ConstBankTurn {
@@ -788,17 +908,32 @@ int dc_unpack_visibility(const uint32_t* records, const int64_t* rank, const int
   return DC_OK;
 }
 
+size_t dc_unpack_compact_workspace(int64_t total_points, int out_elem_size) {
+  return out_elem_size == 1 && total_points > 0 ? sizeof(uint32_t) * (size_t)total_points : 0;
+}
+
 int dc_unpack_visibility_compact(const uint32_t* records, const int64_t* rank, const int64_t* point_off, const int64_t* view_off,
                                  const uint8_t* any_visible, const int64_t* new_index, const int64_t* kept_off,
                                  const int64_t* out_off, int n_scenes, int64_t total_points, int64_t max_points_per_scene,
-                                 void* out, int out_elem_size, dc_stream_t stream) {
+                                 void* out, int out_elem_size, void* workspace, size_t workspace_bytes, dc_stream_t stream) {
   DC_CHECK_ARG(records && rank && point_off && view_off && any_visible && new_index && kept_off && out_off && out,
                "dc_unpack_visibility_compact: null pointer argument");
   DC_CHECK_ARG(out_elem_size == 1 || out_elem_size == 8, "dc_unpack_visibility_compact: out_elem_size must be 1 or 8");
   if (n_scenes <= 0 || max_points_per_scene <= 0) return DC_OK;
   dim3 grid((unsigned)dc::ceil_div<int64_t>(max_points_per_scene, kThreads), (unsigned)n_scenes);
   cudaStream_t st = dc::as_stream(stream);
-  if (out_elem_size == 1)
+  const size_t need = dc_unpack_compact_workspace(total_points, out_elem_size);
+  const bool wide = out_elem_size == 1 && workspace && workspace_bytes >= need && total_points < (1ll << 32) &&
+                    ((uintptr_t)out & 3) == 0;
+  if (wide) {
+    uint32_t* src_pos = static_cast<uint32_t*>(workspace);
+    kept_positions_kernel<<<grid, kThreads, 0, st>>>(rank, point_off, any_visible, new_index, src_pos);
+    DC_LAUNCH_CHECK();
+    const int64_t groups = dc::ceil_div<int64_t>(max_points_per_scene, 4);
+    const int64_t warps = dc::ceil_div<int64_t>(groups, 31);
+    dim3 wgrid((unsigned)dc::ceil_div<int64_t>(warps, kThreads / 32), (unsigned)n_scenes);
+    unpack_compact_wide_kernel<<<wgrid, kThreads, 0, st>>>(records, src_pos, view_off, kept_off, out_off, total_points, (uint8_t*)out);
+  } else if (out_elem_size == 1)
     unpack_kernel<uint8_t, true><<<grid, kThreads, 0, st>>>(records, rank, point_off, view_off, out_off, total_points, any_visible,
                                                             new_index, kept_off, (uint8_t*)out);
   else

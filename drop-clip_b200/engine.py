@@ -450,7 +450,7 @@ class FusionEngine:
         return mask
 
     def compact_visibility(self, b: SceneBatch, any_vis, records, rank, out_dtype=torch.uint8,
-                           extra_rows: Sequence[torch.Tensor] = (), host_sizes: bool = True):
+                           extra_rows: Sequence[torch.Tensor] = (), host_sizes: bool = True, wide_unpack: bool = True):
         """Drops never-visible points and expands the bit records straight into the compacted masks.
         Returns (new_index, kept_off, kept_host, out_off_host, compacted mask, compacted rows).
 
@@ -478,12 +478,14 @@ class FusionEngine:
             mask_elems, n_kept = int(b.off_host["mask"][-1]), n
         cmask_buf = torch.empty(max(mask_elems, 1), dtype=out_dtype, device=b.device)  # empty tensors have a null data_ptr
         cmask = cmask_buf[:mask_elems]
+        uws_bytes = self.lib.dc_unpack_compact_workspace(n, cmask.element_size()) if wide_unpack else 0
+        uws = torch.empty(uws_bytes, dtype=torch.uint8, device=b.device) if uws_bytes else None
         with self._tick("unpack_compact"):
             check(self.lib.dc_unpack_visibility_compact(ptr(records), ptr(rank), ptr(b.off["point"]), ptr(b.off["view"]),
                                                         ptr(any_vis), ptr(new_index), ptr(kept_off), ptr(out_off), b.n_scenes, n,
                                                         max(b.n_points, default=0), ptr(cmask_buf), cmask.element_size(),
-                                                        current_stream()))
-        self.launches += 1
+                                                        ptr(uws), uws_bytes, current_stream()))
+        self.launches += 2 if uws_bytes else 1
         rows_out = []
         for t in extra_rows:
             t2 = t.reshape(n, -1)

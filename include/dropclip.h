@@ -123,7 +123,10 @@ DC_API int dc_unpack_visibility_compact(const uint32_t* records, const int64_t* 
                                  const int64_t* view_off, const uint8_t* any_visible, const int64_t* new_index,
                                  const int64_t* kept_off, const int64_t* out_off, int n_scenes,
                                  int64_t total_points, int64_t max_points_per_scene, void* out,
-                                 int out_elem_size, dc_stream_t stream);
+                                 int out_elem_size, void* workspace, size_t workspace_bytes, dc_stream_t stream);
+/* Optional scratch of dc_unpack_visibility_compact (4 bytes per point for 1-byte masks, else 0): with it the 1-byte
+ * masks are written four columns per thread with 32-bit stores; without it (NULL) one byte per store. Same bytes. */
+DC_API size_t dc_unpack_compact_workspace(int64_t total_points, int out_elem_size);
 
 /* Per-view instance histogram: counts[g*nbins + id] = #pixels of view g with that id,
  * outside[g] = #pixels whose id is not in [0,nbins). Replaces np.unique(seg)

@@ -842,3 +842,29 @@ def test_pixel_level_tile_kernel_vs_oracle(dim, n_objects, sim):
         assert well.mean() > 0.97, f"only {well.mean():.3f} of the rows are well conditioned"
         got, want = got[well], want[well]
     rel_close(got, want, rel=2e-3 if us else REL, what=f"pixel feat tile {dim}")
+
+
+def test_wide_uint8_unpack_equals_byte_unpack_at_every_row_alignment():
+    """The 4-columns-per-thread unpack (32-bit stores, funnel-shifted across threads) must write exactly the bytes of
+    the byte-per-store kernel: scenes whose kept counts make the mask rows start at every alignment, view counts
+    off the 8/32 boundaries, scenes with fewer than four (and with zero) kept points, warps that end inside a row."""
+    from dropclip_b200.engine import FusionEngine, batch_from_device
+    from dropclip_b200.scenes import make_scene
+    eng = FusionEngine("cuda")
+    shapes = [(7001, 6), (130, 5), (33, 33), (1234, 9), (4, 40), (3, 7), (515, 73), (1, 2), (2500, 17)]
+    scenes = [make_scene(900 + i, n_views=v, n_points=n, n_objects=4, device="cuda", as_torch=True)
+              for i, (n, v) in enumerate(shapes)]
+    far = dict(scenes[5])
+    far["points"] = far["points"] + 1e4  # a scene no view sees: zero kept points in the middle of the batch
+    scenes.insert(4, far)
+    b = batch_from_device(scenes, "cuda")
+    records, rank, any_s = eng.visibility_sorted(b, 0.05)
+    _, kept_a, kept_host, off_a, narrow, _ = eng.compact_visibility(b, any_s, records, rank, torch.uint8, wide_unpack=False)
+    _, kept_b, _, off_b, wide, _ = eng.compact_visibility(b, any_s, records, rank, torch.uint8, wide_unpack=True)
+    assert torch.equal(kept_a, kept_b) and np.array_equal(off_a, off_b)
+    kept = np.diff(kept_host)
+    assert kept[4] == 0 and len(set(int(o) % 4 for o in off_a[:-1])) > 1, "the batch should exercise several alignments"
+    assert wide.numel() == narrow.numel() and torch.equal(wide, narrow)
+    # device-resident layout (upper-bound buffers): same bytes in front, nothing written behind
+    _, _, _, off_dev, wide_dev, _ = eng.compact_visibility(b, any_s, records, rank, torch.uint8, host_sizes=False)
+    assert torch.equal(wide_dev[:narrow.numel()], narrow)
