@@ -371,7 +371,12 @@ class PinnedStaging:
         # SPIN for a few milliseconds on every core - exactly the cores the staging helpers of the next upload_list
         # need (measured: the helper calls of one scene took 7.9 ms behind such a copy, 3.3 ms without). A plain
         # single-threaded memcpy through numpy is as fast for these few MB and leaves the cores alone.
-        if t.dtype in _TORCH_TO_NP and not t.is_cuda:
+        nbytes = t.numel() * t.element_size()
+        if not t.is_cuda and nbytes >= (1 << 20):
+            # a few MB (points, colours, labels, object features): the staging pool copies them in 256 KB slices
+            srcs = (ctypes.c_void_p * 1)(t.data_ptr())
+            check(_lib.load().dc_host_gather_copy(srcs, 1, nbytes, ctypes.c_void_p(view.data_ptr()), self._host_threads()))
+        elif t.dtype in _TORCH_TO_NP and not t.is_cuda:
             np.copyto(view.numpy(), t.detach().numpy())
         else:
             view.copy_(t)
