@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libdropclip.so")
 DC_F16, DC_F32, DC_U8, DC_I32, DC_I64, DC_F64 = 0, 1, 2, 3, 4, 5
 DC_SIM_NONE, DC_SIM_MAX, DC_SIM_MEAN = 0, 1, 2
 DC_GROUND_RAW, DC_GROUND_PAIRED, DC_GROUND_ARGMAX = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 P = c_void_p
 # name -> (restype, argtypes); must list every DC_API symbol of include/dropclip.h

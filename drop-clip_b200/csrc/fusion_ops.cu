@@ -309,15 +309,17 @@ __global__ void mask_offsets_kernel(const int64_t* __restrict__ kept_off, const 
   out_off[n_scenes] = run;
 }
 
-// rows of row_bytes (multiple of 4): one thread per 4-byte word
-__global__ void __launch_bounds__(256) compact_rows_kernel(const uint32_t* __restrict__ in, int words_per_row,
+// rows of row_bytes: one thread per unit (4-byte words when the row width and both bases allow it, bytes otherwise, so
+// uint8 colours / labels and fp16 points compact on the device too)
+template <typename U>
+__global__ void __launch_bounds__(256) compact_rows_kernel(const U* __restrict__ in, int units_per_row,
                                                            const uint8_t* __restrict__ flags,
                                                            const int64_t* __restrict__ new_index, int64_t n,
-                                                           uint32_t* __restrict__ out) {
-  const int64_t total = n * words_per_row;
+                                                           U* __restrict__ out) {
+  const int64_t total = n * units_per_row;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t j = t / words_per_row;
-    if (flags[j]) out[new_index[j] * words_per_row + (t - j * words_per_row)] = in[t];
+    const int64_t j = t / units_per_row;
+    if (flags[j]) out[new_index[j] * units_per_row + (t - j * units_per_row)] = in[t];
   }
 }
 
@@ -435,15 +437,20 @@ int dc_compact_mask_offsets(const int64_t* kept_off, const int64_t* view_off, in
 int dc_compact_rows(const void* in, int64_t row_bytes, const uint8_t* any_visible, const int64_t* new_index,
                     int64_t total_points, void* out, dc_stream_t stream) {
   DC_CHECK_ARG(in && any_visible && new_index && out, "dc_compact_rows: null pointer argument");
-  DC_CHECK_ARG(row_bytes > 0 && row_bytes % 4 == 0, "dc_compact_rows: row_bytes must be a positive multiple of 4");
+  DC_CHECK_ARG(row_bytes > 0 && row_bytes <= (1 << 30), "dc_compact_rows: row_bytes must be positive");
   if (total_points <= 0) return DC_OK;
-  const int words = (int)(row_bytes / 4);
-  const int64_t total = total_points * words;
+  const bool words = row_bytes % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 3) == 0;
+  const int units = (int)(words ? row_bytes / 4 : row_bytes);
+  const int64_t total = total_points * units;
   int64_t blocks = dc::ceil_div<int64_t>(total, 256);
   const int64_t cap = (int64_t)dc::sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  compact_rows_kernel<<<(unsigned)blocks, 256, 0, dc::as_stream(stream)>>>((const uint32_t*)in, words, any_visible, new_index,
-                                                                          total_points, (uint32_t*)out);
+  if (words)
+    compact_rows_kernel<uint32_t><<<(unsigned)blocks, 256, 0, dc::as_stream(stream)>>>((const uint32_t*)in, units, any_visible,
+                                                                                      new_index, total_points, (uint32_t*)out);
+  else
+    compact_rows_kernel<uint8_t><<<(unsigned)blocks, 256, 0, dc::as_stream(stream)>>>((const uint8_t*)in, units, any_visible,
+                                                                                     new_index, total_points, (uint8_t*)out);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

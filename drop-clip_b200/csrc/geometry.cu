@@ -12,7 +12,7 @@ namespace {
 
 __global__ void __launch_bounds__(256) backproject_kernel(const float* __restrict__ depths, int n_views, int height, int width,
                                                           const double* __restrict__ k4, int flip_y, int flip_z,
-                                                          const float* __restrict__ poses, double* __restrict__ out) {
+                                                          const double* __restrict__ poses, double* __restrict__ out) {
   const int64_t hw = (int64_t)height * width;
   const int64_t total = hw * n_views;
   const double fx = k4[0], fy = k4[1], cx = k4[2], cy = k4[3];
@@ -34,14 +34,14 @@ __global__ void __launch_bounds__(256) backproject_kernel(const float* __restric
     if (flip_y & 1) py = -py;
     if (flip_z) pz = -pz;
     if (poses) {
-      const float* m = poses + (int64_t)v * 16;
+      const double* m = poses + (int64_t)v * 16;  // fp64 on the device; an fp32 pose upcasts exactly like np.dot does
       double w[3];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        double acc = __dmul_rn((double)m[4 * r], px);
-        acc = __fma_rn((double)m[4 * r + 1], py, acc);
-        acc = __fma_rn((double)m[4 * r + 2], pz, acc);
-        acc = __dadd_rn((double)m[4 * r + 3], acc);
+        double acc = __dmul_rn(m[4 * r], px);
+        acc = __fma_rn(m[4 * r + 1], py, acc);
+        acc = __fma_rn(m[4 * r + 2], pz, acc);
+        acc = __dadd_rn(m[4 * r + 3], acc);
         w[r] = acc;
       }
       px = w[0]; py = w[1]; pz = w[2];
@@ -90,7 +90,7 @@ unsigned grid_for(int64_t n) {
 extern "C" {
 
 int dc_backproject(const float* depths, int n_views, int height, int width, const double* fxfycxcy, int flip_y, int flip_z,
-                   const float* poses, double* out, dc_stream_t stream) {
+                   const double* poses, double* out, dc_stream_t stream) {
   DC_CHECK_ARG(depths && fxfycxcy && out, "dc_backproject: null pointer argument");
   if (n_views <= 0 || height <= 0 || width <= 0) return DC_OK;
   backproject_kernel<<<grid_for((int64_t)n_views * height * width), 256, 0, dc::as_stream(stream)>>>(
@@ -99,11 +99,11 @@ int dc_backproject(const float* depths, int n_views, int height, int width, cons
   return DC_OK;
 }
 
-int dc_transform_points(const double* points, int64_t n, const float* matrix_host, double* out, dc_stream_t stream) {
+int dc_transform_points(const double* points, int64_t n, const double* matrix_host, double* out, dc_stream_t stream) {
   DC_CHECK_ARG(points && matrix_host && out, "dc_transform_points: null pointer argument");
   if (n <= 0) return DC_OK;
   Mat12 M;
-  for (int i = 0; i < 12; ++i) M.m[i] = (double)matrix_host[i];
+  for (int i = 0; i < 12; ++i) M.m[i] = matrix_host[i];
   transform_points_kernel<<<grid_for(n), 256, 0, dc::as_stream(stream)>>>(points, n, M, out);
   DC_LAUNCH_CHECK();
   return DC_OK;

@@ -26,7 +26,7 @@ struct PixParams {
   const double* points;
   const int64_t* point_off;
   const int64_t* view_off;
-  const float* inv_poses;
+  const double* inv_poses;
   const double* intrinsics;
   const int64_t* mask_off;
   const uint8_t* visible;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_kernel(PixParams p) {
   const int n_views = (int)(p.view_off[scene + 1] - v0);
   for (int i = threadIdx.x; i < n_views * 12; i += kThreads) {
     const int v = i / 12, e = i - v * 12;
-    s_cam[i] = (double)__ldg(p.inv_poses + (v0 + v) * 16 + e);
+    s_cam[i] = __ldg(p.inv_poses + (v0 + v) * 16 + e);
   }
   double* s_K = s_cam + n_views * 12;
   if (threadIdx.x < 9) s_K[threadIdx.x] = __ldg(p.intrinsics + (int64_t)scene * 9 + threadIdx.x);
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 2) pixel_fuse_tile_kernel(PixParams 
   const int n_tile = (int)min((int64_t)kTilePts, n_pts - tile0);
   for (int i = threadIdx.x; i < n_views * 12; i += kThreads) {
     const int v = i / 12, e = i - v * 12;
-    s_cam[i] = (double)__ldg(p.inv_poses + (v0 + v) * 16 + e);
+    s_cam[i] = __ldg(p.inv_poses + (v0 + v) * 16 + e);
   }
   double* s_K = s_cam + n_views * 12;
   if (threadIdx.x < 9) s_K[threadIdx.x] = __ldg(p.intrinsics + (int64_t)scene * 9 + threadIdx.x);
@@ -583,7 +583,7 @@ size_t dc_pixel_fuse_workspace(int64_t total_views, int patch_h, int patch_w, in
   return (size_t)total_views * patch_h * patch_w * query_stride(max_queries_per_scene) * sizeof(float);
 }
 
-int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t* view_off, const float* inv_poses,
+int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t* view_off, const double* inv_poses,
                   const double* intrinsics, const int64_t* mask_off, const uint8_t* visible, const void* seg, int seg_dtype,
                   const float* patch_feats, int patch_h, int patch_w, int dim, const float* queries,
                   const int64_t* query_off, int sim_kernel, int norm_feat, int n_scenes, int64_t max_points_per_scene,

@@ -25,14 +25,25 @@ struct RunAcc {
   unsigned cnt;
 };
 
-__device__ __forceinline__ void flush_run(RunAcc& r, unsigned* warp_hist, unsigned& outside, int nbins) {
+// Ids outside [0, nbins) are rare in valid data (a -1 background at most), so they go straight to the view's
+// four global words: [0] pixels with id >= nbins, [1] pixels with id < 0, [2] smallest negative id (init 0),
+// [3] largest negative id stored as id + 2^63 (init 0) - enough to tell whether the negative ids are ONE distinct
+// value, which np.unique(seg)[1:] simply drops (utils/feature_fusion.py:307).
+__device__ __forceinline__ void flush_run(RunAcc& r, unsigned* warp_hist, unsigned long long* outside, int nbins) {
   if (r.cnt) {
-    if (r.cur >= 0 && r.cur < nbins) atomicAdd(warp_hist + r.cur, r.cnt);
-    else outside += r.cnt;
+    if (r.cur >= 0 && r.cur < nbins) {
+      atomicAdd(warp_hist + r.cur, r.cnt);
+    } else if (r.cur >= 0) {
+      atomicAdd(outside, (unsigned long long)r.cnt);
+    } else {
+      atomicAdd(outside + 1, (unsigned long long)r.cnt);
+      atomicMin(reinterpret_cast<long long*>(outside + 2), r.cur);
+      atomicMax(outside + 3, (unsigned long long)r.cur ^ 0x8000000000000000ull);
+    }
   }
 }
 
-__device__ __forceinline__ void push(RunAcc& r, long long id, unsigned* warp_hist, unsigned& outside, int nbins) {
+__device__ __forceinline__ void push(RunAcc& r, long long id, unsigned* warp_hist, unsigned long long* outside, int nbins) {
   if (id == r.cur) {
     ++r.cnt;
   } else {
@@ -43,7 +54,7 @@ __device__ __forceinline__ void push(RunAcc& r, long long id, unsigned* warp_his
 }
 
 template <typename T>
-__device__ __forceinline__ void consume_vector(const int4& raw, RunAcc& run, unsigned* hist, unsigned& outside, int nbins) {
+__device__ __forceinline__ void consume_vector(const int4& raw, RunAcc& run, unsigned* hist, unsigned long long* outside, int nbins) {
   constexpr int VEC = VecOf<T>::n;
   const T* e = reinterpret_cast<const T*>(&raw);
   if (sizeof(T) < 8) {
@@ -72,7 +83,7 @@ __device__ __forceinline__ void consume_vector(const int4& raw, RunAcc& run, uns
 template <typename T>
 __global__ void __launch_bounds__(kThreads) seg_histogram_kernel(const T* __restrict__ seg, int64_t pixels_per_view,
                                                                  int nbins, uint32_t* __restrict__ counts,
-                                                                 uint32_t* __restrict__ outside_out) {
+                                                                 unsigned long long* __restrict__ outside_out) {
   extern __shared__ unsigned s_hist[];  // [nbins]
   const int view = blockIdx.y;
   for (int i = threadIdx.x; i < nbins; i += kThreads) s_hist[i] = 0;
@@ -85,7 +96,7 @@ __global__ void __launch_bounds__(kThreads) seg_histogram_kernel(const T* __rest
   const int64_t n_vec = (pixels_per_view - head) / VEC;
   const int4* body = reinterpret_cast<const int4*>(base + head);
   RunAcc run{-1, 0};
-  unsigned outside = 0;
+  unsigned long long* outside = outside_out + 4 * (int64_t)view;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   for (; i + 3 * stride < n_vec; i += 4 * stride) {
@@ -103,8 +114,6 @@ __global__ void __launch_bounds__(kThreads) seg_histogram_kernel(const T* __rest
       push(run, (long long)base[j], s_hist, outside, nbins);
   }
   flush_run(run, s_hist, outside, nbins);
-  outside = __reduce_add_sync(0xffffffffu, outside);
-  if ((threadIdx.x & 31) == 0 && outside) atomicAdd(outside_out + view, outside);
   __syncthreads();
   for (int b = threadIdx.x; b < nbins; b += kThreads) {
     const unsigned t = s_hist[b];
@@ -116,7 +125,7 @@ __global__ void __launch_bounds__(kThreads) seg_histogram_kernel(const T* __rest
 // each 32-bin chunk and ballots give the ascending rank of every present id. Present ids are ascending, so every
 // id below n_q is preceded only by ids below n_q: its row is simply its rank minus one (the dropped smallest id).
 // (The one-thread-per-view version walked the 256 bins with dependent loads: 36 us for 4672 views.)
-__global__ void __launch_bounds__(128) view_table_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ outside,
+__global__ void __launch_bounds__(128) view_table_kernel(const uint32_t* __restrict__ counts, const unsigned long long* __restrict__ outside,
                                                          const int64_t* __restrict__ feat_off, const int32_t* __restrict__ view_scene,
                                                          const int64_t* __restrict__ view_off, const int64_t* __restrict__ query_off,
                                                          const int64_t* __restrict__ wobj_off, int64_t total_views, int nbins,
@@ -131,9 +140,16 @@ __global__ void __launch_bounds__(128) view_table_kernel(const uint32_t* __restr
   const int v_local = (int)(g - view_off[s]);
   const int64_t r0 = feat_off[g];
   const int64_t n_rows = feat_off[g + 1] - r0;
-  int status = outside[g] ? 1 : 0;  // an id outside [0,nbins): cannot be indexed by the reference either
+  // Ids outside the histogram: an id >= nbins (>= Q) is indexed by the reference's loop and raises IndexError
+  // there (weight_obj[obj, v], :317). Negative ids: ONE distinct negative value is the smallest id of the view and
+  // is dropped by np.unique(seg)[1:] (e.g. a -1 background) - then no id in [0, nbins) is dropped; two or more
+  // distinct negative values would index weight_obj with a negative row (torch wraps it): reported as IndexError.
+  const unsigned long long* o = outside + 4 * g;
+  int status = o[0] ? 1 : 0;
+  const bool has_negative = o[1] != 0;
+  if (has_negative && (long long)o[2] != (long long)(o[3] ^ 0x8000000000000000ull)) status |= 1;
   const uint32_t* c = counts + g * nbins;
-  int seen = 0;   // present ids met so far, the dropped smallest one included
+  int seen = has_negative ? 1 : 0;   // present ids met so far, the dropped smallest one included
   int bound = 0;  // rows bound by this lane
   for (int id0 = 0; id0 < nbins; id0 += 32) {
     const int id = id0 + lane;
@@ -162,9 +178,9 @@ __global__ void __launch_bounds__(128) view_table_kernel(const uint32_t* __restr
 }  // namespace
 
 extern "C" int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_views, int64_t pixels_per_view,
-                                int nbins, uint32_t* counts, uint32_t* outside, dc_stream_t stream) {
+                                int nbins, uint32_t* counts, uint64_t* outside, dc_stream_t stream) {
   DC_CHECK_ARG(seg && counts && outside, "dc_seg_histogram: null pointer argument");
-  DC_CHECK_ARG(nbins > 0 && nbins <= 1024, "dc_seg_histogram: nbins must be in [1,1024]");
+  DC_CHECK_ARG(nbins > 0 && nbins <= 8192, "dc_seg_histogram: nbins must be in [1,8192]");
   DC_CHECK_ARG(seg_dtype == DC_U8 || seg_dtype == DC_I32 || seg_dtype == DC_I64,
                "dc_seg_histogram: seg dtype must be u8, i32 or i64");
   if (total_views <= 0 || pixels_per_view <= 0) return DC_OK;
@@ -173,7 +189,7 @@ extern "C" int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_vi
   DC_CHECK_ARG((uintptr_t)seg % esize == 0, "dc_seg_histogram: seg is not aligned to its element size");
   cudaStream_t st = dc::as_stream(stream);
   DC_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (size_t)total_views * nbins, st));
-  DC_CUDA(cudaMemsetAsync(outside, 0, sizeof(uint32_t) * (size_t)total_views, st));
+  DC_CUDA(cudaMemsetAsync(outside, 0, sizeof(uint64_t) * 4 * (size_t)total_views, st));
   // CTAs of ~512 KB: enough of them per view to fill the machine a few times over when there are few views, and small
   // enough that the last wave does not leave SMs idle when there are many (4672 views of 2.4 MB: one CTA per view
   // ran at 6.9 TB/s, four at 7.3 TB/s)
@@ -185,16 +201,16 @@ extern "C" int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_vi
   dim3 grid(gx, (unsigned)total_views);
   const size_t smem = sizeof(unsigned) * nbins;
   if (seg_dtype == DC_U8)
-    seg_histogram_kernel<uint8_t><<<grid, kThreads, smem, st>>>((const uint8_t*)seg, pixels_per_view, nbins, counts, outside);
+    seg_histogram_kernel<uint8_t><<<grid, kThreads, smem, st>>>((const uint8_t*)seg, pixels_per_view, nbins, counts, (unsigned long long*)outside);
   else if (seg_dtype == DC_I32)
-    seg_histogram_kernel<int32_t><<<grid, kThreads, smem, st>>>((const int32_t*)seg, pixels_per_view, nbins, counts, outside);
+    seg_histogram_kernel<int32_t><<<grid, kThreads, smem, st>>>((const int32_t*)seg, pixels_per_view, nbins, counts, (unsigned long long*)outside);
   else
-    seg_histogram_kernel<long long><<<grid, kThreads, smem, st>>>((const long long*)seg, pixels_per_view, nbins, counts, outside);
+    seg_histogram_kernel<long long><<<grid, kThreads, smem, st>>>((const long long*)seg, pixels_per_view, nbins, counts, (unsigned long long*)outside);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
 
-extern "C" int dc_view_table(const uint32_t* counts, const uint32_t* outside, const int64_t* feat_off,
+extern "C" int dc_view_table(const uint32_t* counts, const uint64_t* outside, const int64_t* feat_off,
                              const int32_t* view_scene, const int64_t* view_off, const int64_t* query_off,
                              const int64_t* wobj_off, int64_t total_views, int64_t total_rows, int64_t total_wobj,
                              int nbins, int32_t* row_object, int32_t* object_row, int32_t* view_status,
@@ -208,7 +224,7 @@ extern "C" int dc_view_table(const uint32_t* counts, const uint32_t* outside, co
   (void)total_rows;
   const int threads = 128;  // four views per CTA, one warp each
   view_table_kernel<<<(unsigned)dc::ceil_div<int64_t>(total_views, threads / 32), threads, 0, st>>>(
-      counts, outside, feat_off, view_scene, view_off, query_off, wobj_off, total_views, nbins, row_object,
+      counts, (const unsigned long long*)outside, feat_off, view_scene, view_off, query_off, wobj_off, total_views, nbins, row_object,
       object_row, view_status);
   DC_LAUNCH_CHECK();
   return DC_OK;

@@ -34,7 +34,7 @@ struct VisParams {
   const int64_t* point_off;
   const int64_t* view_off;
   const float* depths;
-  const float* inv_poses;
+  const double* inv_poses;
   const double* intrinsics;
   const int64_t* mask_off;
   int height, width;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, 4) project_visibility_kernel(VisPara
 }  // namespace
 
 extern "C" int dc_project_visibility(const double* points, const int64_t* point_off, const int64_t* view_off,
-                                     const float* depths, const float* inv_poses, const double* intrinsics,
+                                     const float* depths, const double* inv_poses, const double* intrinsics,
                                      const int64_t* mask_off, int n_scenes, int64_t max_points_per_scene,
                                      int max_views_per_scene, int height, int width, double threshold,
                                      void* mask, int mask_elem_size, uint8_t* any_visible, const void* seg,

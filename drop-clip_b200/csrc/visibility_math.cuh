@@ -107,14 +107,14 @@ __device__ __forceinline__ bool project_point(const double* __restrict__ m, cons
 // Loads the per-scene camera constants into shared memory: [n_views][12] inverse pose rows
 // (fp32 -> fp64, rows 1 and 2 negated) followed by the 9 intrinsics. Returns true when every
 // entry is finite and below kBig and K has the pinhole structure (shortcut (b) allowed).
-__device__ __forceinline__ bool load_cameras(double* s_cam, int* s_ok, const float* __restrict__ inv_poses, int64_t v0, int n_views,
+__device__ __forceinline__ bool load_cameras(double* s_cam, int* s_ok, const double* __restrict__ inv_poses, int64_t v0, int n_views,
                                              const double* __restrict__ intrinsics, int scene) {
   if (threadIdx.x == 0) *s_ok = 1;
   __syncthreads();
   bool mine_ok = true;
   for (int i = threadIdx.x; i < n_views * 12; i += blockDim.x) {
     const int v = i / 12, e = i - v * 12;
-    const double val = (double)__ldg(inv_poses + (v0 + v) * 16 + e);  // fp32 -> fp64 like np.dot's upcast
+    const double val = __ldg(inv_poses + (v0 + v) * 16 + e);  // fp64 on the device: an fp32 inverse upcasts exactly like np.dot does
     mine_ok &= fabs(val) < kBig;
     // (a) round-to-nearest is sign-symmetric, so evaluating the chain with rows 1 and 2 negated gives
     //     exactly the negated camera-frame y and z (only the sign of an exact zero can differ, which

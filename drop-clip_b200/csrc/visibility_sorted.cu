@@ -267,7 +267,7 @@ __host__ __device__ inline double near_limit(int limit) { return 0.5 * (limit - 
 __host__ __device__ inline double coord_bound(int limit) { return 0.5 * (limit - 1) + near_limit(limit) + 1.0; }  // U
 
 // one thread per (scene, view slot): fp64 set-up of the filter constants
-__global__ void camera_prep_kernel(const float* __restrict__ inv_poses, const double* __restrict__ intrinsics,
+__global__ void camera_prep_kernel(const double* __restrict__ inv_poses, const double* __restrict__ intrinsics,
                                    const int64_t* __restrict__ view_off, const float* __restrict__ bbox, int n_scenes,
                                    int max_views, int height, int width, double threshold, ViewConst* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -291,7 +291,7 @@ __global__ void camera_prep_kernel(const float* __restrict__ inv_poses, const do
     bool ok = true;
 #pragma unroll
     for (int e = 0; e < 12; ++e) {
-      const double val = (double)__ldg(inv_poses + (v0 + v) * 16 + e);
+      const double val = __ldg(inv_poses + (v0 + v) * 16 + e);
       ok &= fabs(val) < 1e30;
       m[e] = (e >= 4) ? -val : val;
     }
@@ -355,7 +355,7 @@ struct FastParams {
   const int64_t* point_off;
   const int64_t* view_off;
   const float* depths;
-  const float* inv_poses;
+  const double* inv_poses;
   const double* intrinsics;
   const int64_t* perm;
   int64_t total_points;
@@ -375,7 +375,7 @@ struct FastParams {
 // warp's slice of s_rec. Kept out of line so that its fp64 registers do not weigh on the filter loop.
 // `pts` / `perm` point at the scene's first point, `poses` / `depths` at its first view, `K` at its intrinsics.
 static __device__ __noinline__ void drain_queue(const uint32_t* __restrict__ queue, int count, int n_tile, const double* __restrict__ pts,
-                                                const int64_t* __restrict__ perm_tile, const float* __restrict__ poses,
+                                                const int64_t* __restrict__ perm_tile, const double* __restrict__ poses,
                                                 const double* __restrict__ Kp, const float* __restrict__ depths, int width,
                                                 int height, double threshold, uint32_t* __restrict__ s_rec) {
   const int lane = threadIdx.x & 31;
@@ -391,7 +391,7 @@ static __device__ __noinline__ void drain_queue(const uint32_t* __restrict__ que
     double m[12];
 #pragma unroll
     for (int e = 0; e < 12; ++e) {
-      const double val = (double)__ldg(poses + (int64_t)v * 16 + e);
+      const double val = __ldg(poses + (int64_t)v * 16 + e);
       m[e] = (e >= 4) ? -val : val;
     }
     int pix;
@@ -825,7 +825,7 @@ int dc_spatial_sort(const double* points, const int64_t* point_off, int n_scenes
 }
 
 int dc_project_visibility_sorted(const double* points, const int64_t* point_off, const int64_t* view_off, const float* depths,
-                                 const float* inv_poses, const double* intrinsics, int n_scenes, int64_t total_points,
+                                 const double* inv_poses, const double* intrinsics, int n_scenes, int64_t total_points,
                                  int64_t max_points_per_scene, int max_views_per_scene, int height, int width,
                                  double threshold, uint32_t* records, int64_t* rank, uint8_t* any_visible, void* workspace,
                                  size_t workspace_bytes, dc_stream_t stream) {

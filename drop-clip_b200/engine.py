@@ -24,13 +24,37 @@ from ._lib import check, current_stream, ptr
 _TORCH_TO_NP = {torch.float32: np.dtype(np.float32), torch.float64: np.dtype(np.float64), torch.int64: np.dtype(np.int64),
                 torch.int32: np.dtype(np.int32), torch.uint8: np.dtype(np.uint8), torch.float16: np.dtype(np.float16)}
 SIM_KERNELS = {None: _lib.DC_SIM_NONE, "max": _lib.DC_SIM_MAX, "mean": _lib.DC_SIM_MEAN}
-MAX_BINS = 256  # instance ids are stored as uint8 labels downstream (tools/preprocess_data.py:294)
+MIN_BINS = 256  # instance ids are stored as uint8 labels downstream (tools/preprocess_data.py:294); more bins when Q > 256
+MAX_BINS = MIN_BINS  # kept for callers that size count tables for the common case
+
+
+def hist_bins(max_queries: int) -> int:
+    """Bins of the per-view instance histogram: every id the reference can index (ids < Q, quirk q7) needs one."""
+    return max(MIN_BINS, (int(max_queries) + 31) // 32 * 32)
 
 
 def _prefix(counts: Sequence[int]) -> np.ndarray:
     out = np.zeros(len(counts) + 1, dtype=np.int64)
     np.cumsum(np.asarray(counts, dtype=np.int64), out=out[1:])
     return out
+
+
+def _labels_as_int64(labels) -> np.ndarray:
+    """Point labels as int64 object ids for the scatter kernel. The reference compares `label == obj`
+    (utils/feature_fusion.py:133) in the caller's dtype, so a non-integral or non-finite float label matches no
+    object: it becomes -1 (a zero row) instead of being truncated onto a neighbouring id."""
+    arr = np.asarray(labels).reshape(-1)
+    if arr.dtype == np.int64:
+        return arr
+    if arr.dtype.kind == "f":
+        with np.errstate(invalid="ignore"):
+            ok = np.isfinite(arr) & (arr == np.floor(arr)) & (np.abs(arr) < 2.0 ** 62)
+        return np.where(ok, arr, -1).astype(np.int64)
+    if arr.dtype.kind == "b":
+        return arr.astype(np.int64)
+    if arr.dtype.kind == "u" and arr.dtype.itemsize == 8:
+        return np.where(arr < np.uint64(2 ** 63), arr, np.uint64(0)).astype(np.int64) - (arr >= np.uint64(2 ** 63))
+    return arr.astype(np.int64)
 
 
 def intrinsic_matrix(intr: Dict[str, float]) -> np.ndarray:
@@ -54,7 +78,7 @@ class SceneBatch:
     # device arrays
     points: torch.Tensor  # (sum N, 3) f64
     depths: torch.Tensor  # (TV, H, W) f32
-    inv_poses: torch.Tensor  # (TV, 16) f32
+    inv_poses: torch.Tensor  # (TV, 16) f64 (inverted in the pose dtype on the host, then widened: exact)
     intrinsics: torch.Tensor  # (S, 9) f64
     segs: Optional[torch.Tensor] = None  # (TV, H, W) u8 / i32 / i64
     labels: Optional[torch.Tensor] = None  # (sum N,) i64
@@ -112,7 +136,8 @@ class SceneBatch:
         and optionally labels, seg_masks, mv_features, query_embeddings.
 
         The camera->world poses are inverted here with np.linalg.inv in their own dtype, exactly
-        like utils/transforms.py:54 does on the host (a 4x4 per view)."""
+        like utils/transforms.py:54 does on the host (a 4x4 per view), and stored as fp64 on the device:
+        widening an fp32 inverse is what np.dot does with it (exact), and fp64 poses stay fp64."""
         dev = torch.device(device)
         get = (lambda s, k: s.get(k)) if isinstance(scenes[0], dict) else (lambda s, k: getattr(s, k, None))
         intr0 = get(scenes[0], "intrinsic")
@@ -150,7 +175,8 @@ class SceneBatch:
                 inv = [np.linalg.inv(p) for p in poses]
         else:
             inv = [np.asarray(p) for ps in inv_poses for p in ps]
-        inv = np.stack(inv).astype(np.float32).reshape(-1, 16) if inv else np.zeros((0, 16), np.float32)
+        # np.dot(inv_pose, fp64 points) promotes an fp32 inverse to fp64 (exact); an fp64 pose stays fp64 end to end
+        inv = np.stack([np.asarray(m, dtype=np.float64) for m in inv]).reshape(-1, 16) if inv else np.zeros((0, 16), np.float64)
         K = np.stack([intrinsic_matrix(get(s, "intrinsic")).reshape(9) for s in scenes])
         b = cls(device=dev, height=H, width=W, n_scenes=len(scenes), n_points=n_points, n_views=n_views,
                 n_queries=n_queries, feat_rows=feat_rows, points=up(pts),
@@ -175,7 +201,7 @@ class SceneBatch:
                 else:
                     b.segs = up(np.stack([m.astype(dt, copy=False) for m in segs]))
         if get(scenes[0], "labels") is not None:
-            lab_l = [np.asarray(get(s, "labels")).astype(np.int64, copy=False).reshape(-1) for s in scenes]
+            lab_l = [_labels_as_int64(get(s, "labels")) for s in scenes]
             b.labels = up(lab_l[0] if len(lab_l) == 1 else np.concatenate(lab_l))
         if has_f:
             fl = [f for s in scenes for f in get(s, "mv_features")]
@@ -220,7 +246,7 @@ def batch_from_device(scenes: Sequence[dict], device="cuda", seg_dtype=torch.int
     n_queries = [int(s["query_embeddings"].shape[0]) for s in scenes]
     feat_rows = [int(f.shape[0]) for s in scenes for f in s["mv_features"]]
     host = SceneBatch.offsets_for(n_points, n_views, n_queries, feat_rows)
-    inv = np.stack([np.linalg.inv(p) for s in scenes for p in s["camera_poses"].cpu().numpy()]).astype(np.float32)
+    inv = np.stack([np.linalg.inv(p) for s in scenes for p in s["camera_poses"].cpu().numpy()]).astype(np.float64)
     K = np.stack([intrinsic_matrix(s["intrinsic"]).reshape(9) for s in scenes])
     fdt = scenes[0]["mv_features"][0].dtype
     b = SceneBatch(
@@ -520,18 +546,19 @@ class FusionEngine:
     def seg_tables(self, b: SceneBatch):
         """Instance histograms and the feature-row <-> object binding of every view."""
         tv = b.total_views
-        counts = torch.empty((tv, MAX_BINS), dtype=torch.int32, device=b.device)
-        outside = torch.empty(tv, dtype=torch.int32, device=b.device)
+        nbins = hist_bins(max(b.n_queries, default=0))
+        counts = torch.empty((tv, nbins), dtype=torch.int32, device=b.device)
+        outside = torch.empty((max(tv, 1), 4), dtype=torch.int64, device=b.device)
         with self._tick("seg_histogram"):
             check(self.lib.dc_seg_histogram(ptr(b.segs), _lib.torch_dtype_code(b.segs.dtype), tv, b.height * b.width,
-                                            MAX_BINS, ptr(counts), ptr(outside), current_stream()))
+                                            nbins, ptr(counts), ptr(outside), current_stream()))
         row_object = torch.empty(max(b.total_rows, 1), dtype=torch.int32, device=b.device)
         total_wobj = int(b.off_host["wobj"][-1])
         object_row = torch.empty(max(total_wobj, 1), dtype=torch.int32, device=b.device)
         status = torch.empty(max(tv, 1), dtype=torch.int32, device=b.device)
         check(self.lib.dc_view_table(ptr(counts), ptr(outside), ptr(b.off["feat"]), ptr(b.off["view_scene"]),
                                      ptr(b.off["view"]), ptr(b.off["query"]), ptr(b.off["wobj"]), tv, b.total_rows,
-                                     total_wobj, MAX_BINS, ptr(row_object), ptr(object_row), ptr(status),
+                                     total_wobj, nbins, ptr(row_object), ptr(object_row), ptr(status),
                                      current_stream()))
         self.launches += 2
         return counts, outside, row_object, object_row, status
@@ -560,7 +587,7 @@ class FusionEngine:
                                              ptr(sims), ld, ptr(ws), ws_bytes, current_stream()))
             self.launches += 4
         check(self.lib.dc_view_weights(ptr(sims), ld, ptr(b.off["feat"]), ptr(b.off["view_scene"]), ptr(b.off["view"]),
-                                       ptr(b.off["query"]), ptr(b.off["wobj"]), ptr(row_object), ptr(counts), MAX_BINS,
+                                       ptr(b.off["query"]), ptr(b.off["wobj"]), ptr(row_object), ptr(counts), int(counts.shape[1]),
                                        b.total_views, kern, int(bool(use_visibility)), ptr(weight), current_stream()))
         fused = torch.empty((b.total_queries, dim), dtype=torch.float32, device=b.device)
         with self._tick("segmented_wmean"):
@@ -570,7 +597,21 @@ class FusionEngine:
         self.launches += 2
         return fused, weight
 
+    def compact_rows(self, t: torch.Tensor, any_vis, new_index, n_kept: int) -> torch.Tensor:
+        """out[new_index[j]] = t[j] for the kept points; rows of any byte width."""
+        n = int(any_vis.shape[0])
+        t2 = t.reshape(n, -1)
+        o_buf = torch.empty((max(n_kept, 1), t2.shape[1]), dtype=t.dtype, device=t.device)
+        check(self.lib.dc_compact_rows(ptr(t2), t2.shape[1] * t2.element_size(), ptr(any_vis), ptr(new_index), n, ptr(o_buf),
+                                       current_stream()))
+        self.launches += 1
+        return o_buf[:n_kept]
+
     def scatter_to_points(self, b: SceneBatch, fused, labels, point_off, n_scenes, max_points, skip_first=True):
+        if labels.dtype != torch.int64 or not labels.is_contiguous():
+            raise TypeError(f"scatter_to_points: labels must be a contiguous int64 tensor (got {labels.dtype}); the kernel reads 8 bytes per point")
+        if fused.dtype != torch.float32:
+            raise TypeError("scatter_to_points: fused features must be fp32")
         dim = int(fused.shape[1])
         n_rows = int(labels.shape[0])
         out = torch.empty((max(n_rows, 1), dim), dtype=torch.float32, device=fused.device)

@@ -204,8 +204,9 @@ class MultiviewFeatureFusion:
             elif name == "labels" and isinstance(arr, np.ndarray) and arr.dtype == np.int64:
                 b.row_sources[name] = b.labels.view(-1, 1)
             elif isinstance(arr, np.ndarray) and arr.ndim >= 1 and arr.shape[0] == n_pts and n_pts > 0 and \
-                    arr.dtype in (np.float64, np.float32, np.float16, np.int64, np.int32, np.int16, np.int8, np.uint8):
-                b.row_sources[name] = staging.upload(np.ascontiguousarray(arr).reshape(n_pts, -1))
+                    arr.dtype.kind in "fiub" and arr.size > 0:
+                # any fixed-width dtype travels as raw bytes (uint8 colours, int32 / uint8 labels, fp16 points ...)
+                b.row_sources[name] = staging.upload(np.ascontiguousarray(arr).reshape(n_pts, -1).view(np.uint8))
         staging.end()
         return b
 
@@ -254,8 +255,12 @@ class MultiviewFeatureFusion:
         mv_feats_obj = res["fused"]
         if not return_obj:
             k_off = torch.tensor([0, n_kept], dtype=torch.int64, device=eng.device)
-            lab_dev = rows_out[names.index("labels")].view(-1) if "labels" in names else \
-                torch.from_numpy(np.asarray(labels).take(keep, axis=0).astype(np.int64).reshape(-1)).to(eng.device)
+            # the scatter kernel reads int64 ids: compact the batch's own int64 copy of the labels, never the caller's
+            # raw rows (int32 / uint8 / float labels are returned in their dtype but must not be reinterpreted)
+            if "labels" in names and dev_rows["labels"].dtype == torch.int64:
+                lab_dev = rows_out[names.index("labels")].reshape(-1)
+            else:
+                lab_dev = eng.compact_rows(b.labels, res["any_visible"], new_index, n_kept).reshape(-1)
             mv_feats = eng.scatter_to_points(b, mv_feats_obj, lab_dev, k_off, 1, n_kept, skip_first=True).cpu()
         else:
             mv_feats = mv_feats_obj
@@ -263,7 +268,7 @@ class MultiviewFeatureFusion:
         final = []
         for name, arr in host_rows.items():
             if name in outs:
-                final.append(outs[name].numpy().reshape((n_kept,) + tuple(np.shape(arr)[1:])))
+                final.append(outs[name].numpy().view(arr.dtype).reshape((n_kept,) + tuple(np.shape(arr)[1:])))
             else:
                 final.append(arr.take(keep, axis=0) if isinstance(arr, np.ndarray) else np.asarray(arr)[keep])
         return (mv_feats, weight_obj, visibility_mask), tuple(final)

@@ -102,8 +102,8 @@ def aggregate_views_blender_new(scene, camera_intrinsic, depth_trunc=25.0, voxel
         keep = (d0 > 0).reshape(-1)                     # Open3D keeps 0 < depth < trunc
         pts = backproject(d0, camera_intrinsic, o3d_rounding=True)[0].reshape(-1, 3)[keep]
         pts = (pts * torch.tensor([1.0, -1.0, -1.0], dtype=torch.float64, device=dev)).contiguous()  # pc.transform(T_cam)
-        # camera -> world with the view's fp32 world_matrix promoted to fp64 (utils/geometry.py:163-164)
-        world = np.ascontiguousarray(np.asarray(stuff["camera"]["world_matrix"]), dtype=np.float32).reshape(16)
+        # camera -> world with the view's world_matrix as fp64 (`.astype(np.float64)`, utils/geometry.py:163-164)
+        world = np.ascontiguousarray(np.asarray(stuff["camera"]["world_matrix"]), dtype=np.float64).reshape(16)
         out = torch.empty_like(pts)
         check(_lib.load().dc_transform_points(ptr(pts), pts.shape[0], world.ctypes.data_as(_lib.c_void_p), ptr(out),
                                               current_stream()))

@@ -52,7 +52,7 @@ def transform_points(pointcloud, matrix) -> np.ndarray:
     lib = _lib.load()
     pts = torch.from_numpy(np.ascontiguousarray(pointcloud, dtype=np.float64).reshape(-1, 3)).to(_dev())
     out = torch.empty_like(pts)
-    m = np.ascontiguousarray(np.asarray(matrix), dtype=np.float32).reshape(16)
+    m = np.ascontiguousarray(np.asarray(matrix), dtype=np.float64).reshape(16)  # np.dot promotes to fp64 (points4 is fp64)
     check(lib.dc_transform_points(ptr(pts), pts.shape[0], m.ctypes.data_as(_lib.c_void_p), ptr(out), current_stream()))
     return out.cpu().numpy()
 
@@ -78,7 +78,7 @@ def backproject(depth_images, camera_intrinsics, flip_y=False, flip_z=False, pos
     out = torch.empty((V, H, W, 3), dtype=torch.float64, device=d.device)
     p = None
     if poses is not None:
-        p = torch.from_numpy(np.ascontiguousarray(np.asarray(poses), dtype=np.float32).reshape(V, 16)).to(d.device)
+        p = torch.from_numpy(np.ascontiguousarray(np.asarray(poses), dtype=np.float64).reshape(V, 16)).to(d.device)
     check(lib.dc_backproject(ptr(d), V, H, W, ptr(_k4(camera_intrinsics)), int(bool(flip_y)) | (2 if o3d_rounding else 0), int(flip_z), ptr(p), ptr(out),
                              current_stream()))
     return out

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 1
+#define DC_ABI_VERSION 2
 #if defined(__GNUC__)
 #define DC_API __attribute__((visibility("default")))
 #else
@@ -77,11 +77,13 @@ DC_API int dc_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l
  * and writes mask[mask_off[s] + v*N_s + i] (uint8 or int64, selected by mask_elem_size).
  * Optional outputs (NULL to skip): any_visible[j] = OR over views; point_object[same layout
  * as mask] = seg[g][v,u] for visible points, -1 otherwise (needs `seg`).
- * The inverse pose is an input (16 fp32 per view, row-major) because the reference inverts in
- * fp32 with LAPACK on the host (np.linalg.inv, utils/transforms.py:54).
+ * The inverse pose is an input (16 fp64 per view, row-major) because the reference inverts with
+ * LAPACK on the host in the POSE's dtype (np.linalg.inv, utils/transforms.py:54) and np.dot then promotes an
+ * fp32 inverse to fp64 exactly; the host side inverts in the caller's dtype and widens, so fp32 and fp64
+ * poses both reproduce the reference bit for bit.
  */
 DC_API int dc_project_visibility(const double* points, const int64_t* point_off, const int64_t* view_off,
-                          const float* depths, const float* inv_poses, const double* intrinsics,
+                          const float* depths, const double* inv_poses, const double* intrinsics,
                           const int64_t* mask_off, int n_scenes, int64_t max_points_per_scene,
                           int max_views_per_scene, int height, int width, double threshold,
                           void* mask, int mask_elem_size, uint8_t* any_visible,
@@ -104,7 +106,7 @@ DC_API size_t dc_visibility_sorted_workspace(int64_t total_points, int n_scenes,
 /* number of filter-kernel launches dc_project_visibility_sorted issues for these extents (launch accounting) */
 DC_API int dc_visibility_sorted_groups(int n_scenes, int64_t max_points_per_scene, int max_views_per_scene);
 DC_API int dc_project_visibility_sorted(const double* points, const int64_t* point_off, const int64_t* view_off,
-                                 const float* depths, const float* inv_poses, const double* intrinsics,
+                                 const float* depths, const double* inv_poses, const double* intrinsics,
                                  int n_scenes, int64_t total_points, int64_t max_points_per_scene,
                                  int max_views_per_scene, int height, int width, double threshold,
                                  uint32_t* records, int64_t* rank, uint8_t* any_visible, void* workspace,
@@ -128,11 +130,13 @@ DC_API int dc_unpack_visibility_compact(const uint32_t* records, const int64_t* 
  * masks are written four columns per thread with 32-bit stores; without it (NULL) one byte per store. Same bytes. */
 DC_API size_t dc_unpack_compact_workspace(int64_t total_points, int out_elem_size);
 
-/* Per-view instance histogram: counts[g*nbins + id] = #pixels of view g with that id,
- * outside[g] = #pixels whose id is not in [0,nbins). Replaces np.unique(seg)
- * utils/feature_fusion.py:307 and (seg == obj).sum() :320. seg_dtype: DC_U8 / DC_I32 / DC_I64. */
+/* Per-view instance histogram: counts[g*nbins + id] = #pixels of view g with that id (nbins <= 8192; the host
+ * side uses max(256, max Q) so that every id the reference can index has a bin). outside[4*g ..]: [0] #pixels with
+ * id >= nbins, [1] #pixels with id < 0, [2] smallest negative id (int64, 0 if none), [3] largest negative id
+ * + 2^63 (0 if none). Replaces np.unique(seg) utils/feature_fusion.py:307 and (seg == obj).sum() :320.
+ * seg_dtype: DC_U8 / DC_I32 / DC_I64. */
 DC_API int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_views, int64_t pixels_per_view,
-                     int nbins, uint32_t* counts, uint32_t* outside, dc_stream_t stream);
+                     int nbins, uint32_t* counts, uint64_t* outside, dc_stream_t stream);
 
 /* Binds feature rows to object ids the way the reference's loop does (utils/feature_fusion.py
  * :307,315,333): the ids present in a view, ascending, minus the smallest one; row i of the
@@ -140,9 +144,10 @@ DC_API int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_views,
  *   feat_off   [total_views+1] first feature row of each view
  *   view_scene [total_views]   scene of each view;   view_off / query_off / wobj_off [n_scenes+1]
  * Outputs: row_object[total_rows] (id or -1), object_row[wobj layout: wobj_off[s] + id*V_s + v]
- * (global row or -1), view_status[total_views] bit0: an id outside [0,Q_s) is present (the
- * reference raises IndexError), bit1: fewer feature rows than ids (IndexError as well). */
-DC_API int dc_view_table(const uint32_t* counts, const uint32_t* outside, const int64_t* feat_off,
+ * (global row or -1), view_status[total_views] bit0: an id the reference's loop would index lies outside
+ * [0,Q_s) (IndexError there; a single distinct negative id, e.g. a -1 background, is the dropped smallest id and
+ * is fine), bit1: fewer feature rows than ids (IndexError as well). */
+DC_API int dc_view_table(const uint32_t* counts, const uint64_t* outside, const int64_t* feat_off,
                   const int32_t* view_scene, const int64_t* view_off, const int64_t* query_off,
                   const int64_t* wobj_off, int64_t total_views, int64_t total_rows, int64_t total_wobj,
                   int nbins, int32_t* row_object, int32_t* object_row, int32_t* view_status,
@@ -235,7 +240,7 @@ DC_API int dc_compact_mask(const void* mask, int elem_size, const int64_t* mask_
  *               interpolated with the same bicubic weights (then divided by |f| under norm_feat)
  */
 DC_API int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t* view_off,
-                  const float* inv_poses, const double* intrinsics, const int64_t* mask_off,
+                  const double* inv_poses, const double* intrinsics, const int64_t* mask_off,
                   const uint8_t* visible, const void* seg, int seg_dtype, const float* patch_feats, int patch_h,
                   int patch_w, int dim, const float* queries, const int64_t* query_off, int sim_kernel,
                   int norm_feat, int n_scenes, int64_t max_points_per_scene, int max_views_per_scene,
@@ -315,18 +320,18 @@ DC_API int dc_minmax_threshold(float* values, int64_t n, const float* minmax, in
  */
 /* depth_to_pointcloud utils/projections.py:67-86 (+ optional axis flips :89-97 and cam->world
  * utils/transforms.py:43-49): out[v, y, x, :] fp64. flip_y bit0 / flip_z negate after back-projection;
- * flip_y bit1 selects Open3D's rounding order (u - cx) * z / fx; poses (fp32 [n_views,16],
- * camera->world) may be NULL. */
+ * flip_y bit1 selects Open3D's rounding order (u - cx) * z / fx; poses (fp64 [n_views,16],
+ * camera->world, widened from the caller's dtype) may be NULL. */
 DC_API int dc_backproject(const float* depths, int n_views, int height, int width, const double* fxfycxcy,
-                   int flip_y, int flip_z, const float* poses, double* out, dc_stream_t stream);
+                   int flip_y, int flip_z, const double* poses, double* out, dc_stream_t stream);
 /* pointcloud_to_pixel utils/projections.py:59-64: un-truncated fp64 pixel coordinates. */
 DC_API int dc_points_to_pixels(const double* cam_points, int64_t n, const double* fxfycxcy, double* pixels,
                         dc_stream_t stream);
 
 /* Rigid transform out[i,:] = (M . [p_i;1])[:3] in fp64 with np.dot's operation order;
- * M: 16 fp32 (host pointer, row-major). Replaces transform_pointcloud_to_world_frame /
+ * M: 16 fp64 (host pointer, row-major; an fp32 matrix widens exactly like np.dot's promotion). Replaces transform_pointcloud_to_world_frame /
  * _to_camera_frame utils/transforms.py:43-61 (the caller inverts the pose for the latter). */
-DC_API int dc_transform_points(const double* points, int64_t n, const float* matrix_host, double* out,
+DC_API int dc_transform_points(const double* points, int64_t n, const double* matrix_host, double* out,
                         dc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

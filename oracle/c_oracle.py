@@ -33,11 +33,11 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def visibility_view(points, depth, inv_pose32, K, threshold=0.05, want_pixels=False):
+def visibility_view(points, depth, inv_pose, K, threshold=0.05, want_pixels=False):
     """One view: returns mask (N,) int64 [, pixels (N,2) int64, zdepth (N,) fp64]."""
     pts = np.ascontiguousarray(points, dtype=np.float64)
     dep = np.ascontiguousarray(depth, dtype=np.float32)
-    inv = np.ascontiguousarray(inv_pose32, dtype=np.float32)
+    inv = np.ascontiguousarray(inv_pose, dtype=np.float64)  # fp32 inverses widen exactly, fp64 ones stay
     Kc = np.ascontiguousarray(K, dtype=np.float64)
     n = pts.shape[0]
     mask = np.empty(n, dtype=np.int64)
@@ -50,7 +50,7 @@ def visibility_view(points, depth, inv_pose32, K, threshold=0.05, want_pixels=Fa
 
 
 def visibility_mask(points, depths, poses, K, threshold=0.05, inv_poses=None):
-    """(V,N) int64. `poses` are camera->world fp32 matrices; the inverse is taken with
+    """(V,N) int64. `poses` are camera->world matrices (fp32 in production, fp64 allowed); the inverse is taken with
     np.linalg.inv in the pose dtype exactly like utils/transforms.py:54 unless `inv_poses`
     (already inverted, e.g. stored in a golden file) is given."""
     rows = []
@@ -58,6 +58,15 @@ def visibility_mask(points, depths, poses, K, threshold=0.05, inv_poses=None):
         inv = inv_poses[v] if inv_poses is not None else np.linalg.inv(poses[v])
         rows.append(visibility_view(points, depth, inv, K, threshold))
     return np.stack(rows)
+
+
+def transform(points, matrix):
+    """(matrix . [p;1])[:3] per point in fp64 (utils/transforms.py:43-61); the matrix is widened to fp64 like np.dot does."""
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    M = np.ascontiguousarray(matrix, dtype=np.float64).reshape(16)
+    out = np.empty_like(pts)
+    lib().oracle_transform(_p(pts), ctypes.c_int64(pts.shape[0]), _p(M), _p(out))
+    return out
 
 
 def seg_counts(seg, nbins):

@@ -26,13 +26,14 @@ static int64_t trunc_like_numpy(double x) {
   return (int64_t)x;
 }
 
-/* One view. inv_pose: 16 floats (row-major inverse camera->world matrix, already inverted in
- * fp32 by np.linalg.inv), K: 9 doubles row-major. Outputs may be NULL. */
+/* One view. inv_pose: 16 doubles (row-major inverse camera->world matrix, already inverted by np.linalg.inv in
+ * the pose's own dtype and widened - np.dot promotes an fp32 inverse to fp64, utils/transforms.py:54-58),
+ * K: 9 doubles row-major. Outputs may be NULL. */
 void oracle_visibility(const double* pts, int64_t n, const float* depth, int64_t height, int64_t width,
-                       const float* inv_pose, const double* K, double threshold,
+                       const double* inv_pose, const double* K, double threshold,
                        int64_t* mask, int64_t* pix, double* zdepth) {
   double m[12];
-  for (int i = 0; i < 12; ++i) m[i] = (double)inv_pose[i];
+  for (int i = 0; i < 12; ++i) m[i] = inv_pose[i];
   for (int64_t i = 0; i < n; ++i) {
     const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
     double c[3];
@@ -82,4 +83,18 @@ int64_t oracle_seg_counts(const int64_t* seg, int64_t npix, int64_t nbins, int64
 /* floor(xyz / size) in fp32 (true division), converted to int32 like torch's .int(). */
 void oracle_quantize(const float* xyz, int64_t n3, float size, int32_t* out) {
   for (int64_t i = 0; i < n3; ++i) out[i] = (int32_t)floorf(xyz[i] / size);
+}
+
+/* transform_pointcloud_to_world_frame / _to_camera_frame utils/transforms.py:43-61: rows 0..2 of np.dot(M, [p;1])
+ * with M (4x4, 16 doubles row-major: an fp32 matrix is promoted by np.dot) - the same k-ascending FMA chain. */
+void oracle_transform(const double* pts, int64_t n, const double* M, double* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    for (int r = 0; r < 3; ++r) {
+      double acc = M[4 * r] * x;
+      acc = fma(M[4 * r + 1], y, acc);
+      acc = fma(M[4 * r + 2], z, acc);
+      out[3 * i + r] = fma(M[4 * r + 3], 1.0, acc);
+    }
+  }
 }

@@ -339,14 +339,18 @@ def test_seg_histogram_all_dtypes(dtype):
         seg[3, 7] = -4
     t = torch.from_numpy(seg).to(dtype).cuda()
     counts = torch.empty((V, nb), dtype=torch.int32, device="cuda")
-    outside = torch.empty(V, dtype=torch.int32, device="cuda")
+    outside = torch.empty((V, 4), dtype=torch.int64, device="cuda")
     _lib.check(lib.dc_seg_histogram(_lib.ptr(t), _lib.torch_dtype_code(dtype), V, HW, nb, _lib.ptr(counts), _lib.ptr(outside),
                                    _lib.current_stream()))
     torch.cuda.synchronize()
     for v in range(V):
         want, out = c_oracle.seg_counts(seg[v], nb)
         assert np.array_equal(counts[v].cpu().numpy().astype(np.int64), want)
-        assert int(outside[v]) == out
+        assert int(outside[v, 0]) + int(outside[v, 1]) == out  # ids >= nbins and ids < 0
+        neg = seg[v][seg[v] < 0] if dtype != torch.uint8 else np.zeros(0, np.int64)
+        assert int(outside[v, 1]) == neg.size
+        if neg.size:
+            assert int(outside[v, 2]) == neg.min() and int(outside[v, 3]) - 2 ** 63 == neg.max()
 
 
 @pytest.mark.parametrize("name", ["pixel_p0.npz", "pixel_p1.npz"])

@@ -28,7 +28,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert exported == declared, (set(declared) ^ set(exported))
     assert sorted(_lib.SIGNATURES) == declared
     lib = _lib.load()
-    assert lib.dc_abi_version() == 1
+    assert lib.dc_abi_version() == 2
     assert lib.dc_last_error() is not None
     # pure host queries only: no compute call without a GPU
     assert lib.dc_view_score_ld(21) == 32 and lib.dc_view_score_ld(200) == 256
@@ -122,8 +122,12 @@ def test_reference_signatures_are_mirrored():
 def test_shard_tables():
     from dropclip_b200 import shard
     assert shard.strided_shard(10, 1, 4) == [1, 5, 9]
+    # tools/preprocess_data.py:711-716: chunk = ceil((110 - 100) / 3) = 4, inclusive ranges that share their boundary id
+    assert shard.reference_chunks(100, 110, 3) == [(100, 104), (104, 108), (108, 110)]
     parts = [shard.contiguous_shard(100, 110, r, 3) for r in range(3)]
-    assert sum(parts, []) == list(range(100, 111)) and [len(p) for p in parts] == [3, 3, 5]
+    assert sum(parts, []) == list(range(100, 111)) and [len(p) for p in parts] == [5, 4, 2]
+    for r, (lo, hi) in enumerate(shard.reference_chunks(100, 110, 3)):  # each rank stays inside the reference's range
+        assert set(parts[r]) <= set(range(lo, hi + 1))
     bal = shard.balanced_shard([9, 1, 1, 1, 8, 2, 2, 2], 2)
     assert sorted(sum(bal, [])) == list(range(8))
     loads = [sum([9, 1, 1, 1, 8, 2, 2, 2][i] for i in b) for b in bal]
@@ -136,10 +140,14 @@ def test_scene_writer_restart_semantics(tmp_path):
     per_obj[0] = np.nan
     q = np.ones((4, 8), np.float32)
     p = shard.write_scene(str(tmp_path), 12, per_obj, q, np.zeros((5, 3)), np.zeros((5, 3)), np.arange(5), np.ones((2, 5)))
-    z = np.load(p)
+    z = shard.read_scene(p)
     assert np.array_equal(z["multiview/per_obj"][0], q[0]) and np.array_equal(z["multiview/per_obj"][1:], per_obj[1:])
     assert z["pointcloud/label"].dtype == np.uint8 and z["pointcloud/vis_mask"].dtype == np.float32
+    assert z["multiview/obj_ids"].dtype == np.uint8 and z["pointcloud/xyz"].dtype == np.float32
     assert shard.pending_scenes(str(tmp_path), [11, 12, 13]) == [11, 13]
+    # a file the REFERENCE wrote (tools/preprocess_data.py:191 names it {id}.h5py) is honoured by the restart check
+    open(str(tmp_path / "000013.h5py"), "wb").close()
+    assert shard.pending_scenes(str(tmp_path), [11, 12, 13]) == [11]
 
 
 def _gloo_worker(rank, world, port, q):

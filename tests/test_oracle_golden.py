@@ -139,10 +139,25 @@ def test_grounding_matches_reference(case, dname):
 
 
 def test_paired_closed_form_equals_softmax():
-    raw = torch.randn(1000, 9) * 0.3
+    # seeded (numpy stream: stable across machines); exp() of the two forms rounds differently, a few fp32 ulps apart
+    raw = torch.from_numpy(np.random.default_rng(20260118).standard_normal((1000, 9)).astype(np.float32)) * 0.3
     a = similarity_ref.paired_softmax(raw)
     b = similarity_ref.paired_closed_form(raw)
-    np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=2e-6)
+    np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=5e-6)
+
+
+def test_c_transform_is_np_dot():
+    """oracle_transform (visibility_ref.c) == np.dot(M, [p;1])[:3] on this host, for fp64 and promoted fp32 matrices, and ==
+    the golden output of the unmodified transform_pointcloud_to_world_frame."""
+    z = gio.load("proj.npz")
+    np.testing.assert_array_equal(c_oracle.transform(z["regrad"], z["pose"]), z["world"])
+    np.testing.assert_array_equal(c_oracle.transform(z["world"], np.linalg.inv(z["pose"])), z["cam"])
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-9, 9, size=(513, 3))
+    M = rng.standard_normal((4, 4))
+    for mat in (M, M.astype(np.float32)):
+        want = np.dot(mat, np.vstack([pts.T, np.ones((1, pts.shape[0]))]))[:3, :].T
+        np.testing.assert_array_equal(c_oracle.transform(pts, mat), want)
 
 
 def test_projection_helpers_match_reference():
@@ -197,3 +212,19 @@ def test_restatement_against_live_reference():
     cm = c_oracle.visibility_mask(sc.points, sc.depths, sc.camera_poses, K)
     full = M.get_visibility_mask(sc.points, sc.depths, sc.camera_poses).numpy()
     assert np.array_equal(cm, full)
+
+
+@pytest.mark.needs_reference
+def test_c_visibility_with_fp64_poses_against_live_reference():
+    """utils/transforms.py:54-58 inverts and multiplies in the pose's dtype: the C oracle fed the fp64 inverse must
+    reproduce the unmodified reference on fp64 poses (and differ from the run on their fp32 roundings)."""
+    ff, _, _, _ = ref_shim.load()
+    sc, poses64, pts = gio.fp64_pose_case()
+    poses32 = [p.astype(np.float32) for p in poses64]
+    M = ff.MultiviewFeatureFusion(sc.intrinsic, image_size=(120, 160), use_similarity=False, device="cpu")
+    K = fusion_ref.intrinsic_matrix(sc.intrinsic)
+    ref64 = M.get_visibility_mask(pts, sc.depths, poses64).numpy()
+    ref32 = M.get_visibility_mask(pts, sc.depths, poses32).numpy()
+    assert np.array_equal(c_oracle.visibility_mask(pts, sc.depths, poses64, K), ref64)
+    assert np.array_equal(c_oracle.visibility_mask(pts, sc.depths, poses32, K), ref32)
+    assert (ref64 != ref32).sum() > 100, "the case must distinguish fp64 poses from their fp32 roundings"
