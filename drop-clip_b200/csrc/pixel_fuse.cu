@@ -41,7 +41,7 @@ struct PixParams {
   const int64_t* perm;
   float* out_sum;
   float* out_weight;
-  float* dots;   // [total_views][ph * pw][q_stride]: patch row . query, see patch_query_dots_kernel
+  double* dots;  // [total_views][ph * pw][q_stride] fp64: patch row . query, see patch_query_dots_kernel
   int q_stride;
   int normalize;  // divide the sums by sum_v weight (similarity) or by the number of views that see the point
 };
@@ -61,6 +61,46 @@ __device__ __forceinline__ void cubic_taps(int dst, float scale, int in_size, in
   w[3] = cubic2(2.f - t, A);
 #pragma unroll
   for (int k = 0; k < 4; ++k) idx[k] = min(max(i0 - 1 + k, 0), in_size - 1);
+}
+
+// The same taps with fp64 weights (ATen's formulas evaluated in double precision, as F.interpolate does for fp64
+// input): used for the similarity chain only, see "similarity weights in fp64" below.
+__device__ __forceinline__ double cubic1d(double x, double A) { return ((A + 2.0) * x - (A + 3.0)) * x * x + 1.0; }
+__device__ __forceinline__ double cubic2d(double x, double A) { return ((A * x - 5.0 * A) * x + 8.0 * A) * x - 4.0 * A; }
+__device__ __forceinline__ int cubic_weights64(int dst, int in_size, int out_size, double (&w)[4]) {
+  const double A = -0.75;
+  const double src = ((double)in_size / (double)out_size) * ((double)dst + 0.5) - 0.5;
+  const double fl = floor(src);
+  const double t = src - fl;
+  w[0] = cubic2d(t + 1.0, A);
+  w[1] = cubic1d(t, A);
+  w[2] = cubic1d(1.0 - t, A);
+  w[3] = cubic2d(2.0 - t, A);
+  return (int)fl;  // first tap is at index i0 - 1 (clamped by the caller)
+}
+// Taps of one axis with EXACT weights: the fp64 coefficients (for the similarity chain) and their fp32 roundings
+// (for the fp32 feature fold). ATen's own fp32 evaluation of `scale * (dst + 0.5) - 0.5` carries an absolute error
+// of ~1e-6 in the source coordinate (and depends on how its compiler contracted the expression into FMAs), which
+// moves interpolated features by ~2e-7 - already 1e-3 of the smallest magnitudes the parity metric resolves
+// (profiles/r02_reference_fp32_noise.md). Evaluating the coordinate in fp64 puts this kernel next to the exact
+// value of the reference's formula rather than next to one particular build's rounding of it.
+__device__ __forceinline__ void cubic_taps_exact(int dst, int in_size, int out_size, int (&idx)[4], float (&w)[4], double (&w64)[4]) {
+  const int i0 = cubic_weights64(dst, in_size, out_size, w64);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    idx[k] = min(max(i0 - 1 + k, 0), in_size - 1);
+    w[k] = (float)w64[k];
+  }
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
 }
 
 __device__ __forceinline__ int seg_at(const void* seg, int dtype, int64_t idx) {
@@ -85,23 +125,23 @@ __global__ void __launch_bounds__(kThreads) patch_query_dots_kernel(PixParams p)
   const int64_t n_cells = (int64_t)p.ph * p.pw, n_rows = n_cells * n_views;
   for (int64_t r = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); r < n_rows; r += (int64_t)gridDim.x * kWarps) {
     const float* row = p.patch + (v0 * n_cells + r) * p.dim;
-    float* out = p.dots + (v0 * n_cells + r) * p.q_stride;
+    double* out = p.dots + (v0 * n_cells + r) * p.q_stride;
     float t[kMaxPerLane];
 #pragma unroll
     for (int k = 0; k < kMaxPerLane; ++k) t[k] = (k * 32 + lane < p.dim) ? __ldg(row + k * 32 + lane) : 0.f;
     for (int o = 0; o < n_q; o += 4) {  // four queries per round: their loads overlap (the kernel is latency-bound)
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      double d[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (o + j < n_q) {
           const float* qo = q + (int64_t)(o + j) * p.dim;
 #pragma unroll
           for (int k = 0; k < kMaxPerLane; ++k)
-            if (k * 32 + lane < p.dim) d[j] = fmaf(t[k], __ldg(qo + k * 32 + lane), d[j]);
+            if (k * 32 + lane < p.dim) d[j] = fma((double)t[k], (double)__ldg(qo + k * 32 + lane), d[j]);
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) d[j] = dc::warp_sum(d[j]);
+      for (int j = 0; j < 4; ++j) d[j] = warp_sum_d(d[j]);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (lane == 0 && o + j < n_q) out[o + j] = d[j];
@@ -109,43 +149,53 @@ __global__ void __launch_bounds__(kThreads) patch_query_dots_kernel(PixParams p)
   }
 }
 
-// Similarity weight of one visible (point, view) from the dot table, in two phases. interp_dot: lane l interpolates
-// query o0 + l's dots with the same 16 bicubic weights as the feature (issued BEFORE the tap loads, so the tap
-// coordinates are dead once the feature is formed). finish_weight: divides by |f| under norm_feat and returns
-// clip(pos - max|mean(neg), 1e-6) (calculate_sim, feature_fusion.py:65-73). Scenes with more than 32 queries
-// take further rounds of interp_dot inside finish_weight.
-__device__ __forceinline__ float interp_dot(const PixParams& p, const float* __restrict__ dots_view, const int (&iy)[4],
-                                            const int (&ix)[4], const float (&wy)[4], const float (&wx)[4], int o, int n_q) {
-  float mine = 0.f;
+// Similarity weights in fp64. The weight of a visible (point, view) is clip(pos - max|mean(neg), 1e-6) of the
+// similarities of its (normalised) interpolated feature with the scene's queries (calculate_sim,
+// feature_fusion.py:65-73,182-196). On surfaces whose best two queries tie, pos - neg is a difference of two numbers
+// ~1 that lands near the 1e-6 clip, and the fused feature of a point whose views all do that is a mean with weights
+// of relative accuracy eps_fp32 / 1e-6: the reference's own fp32 result is then several percent away from the exact
+// value of its formulas (profiles/r02_reference_fp32_noise.md: 0.7 % of the rows of a 480x640, V=8 scene are off by
+// more than 1e-3). An fp32 evaluation here would add its own, different, noise on top, so the whole chain is exact
+// instead: fp64 (patch . query) table, fp64 bicubic weights, pos - red(neg) in fp64, ONE division by |f| at the end
+// ((pos - neg) / |f| = pos / |f| - neg / |f|, and max commutes with the positive scale), one rounding to fp32.
+// What remains between this and the reference is the reference's rounding noise alone.
+// interp_dot: lane l interpolates query o's dots (issued before the tap loads); finish_weight reduces over queries.
+// Scenes with more than 32 queries take further rounds of interp_dot inside finish_weight.
+__device__ __forceinline__ double interp_dot(const PixParams& p, const double* __restrict__ dots_view, const int (&iy)[4],
+                                             const int (&ix)[4], const double (&wy)[4], const double (&wx)[4], int o, int n_q) {
+  double mine = 0.0;
   if (o < n_q) {
 #pragma unroll
     for (int ty = 0; ty < 4; ++ty) {
-      const float* row = dots_view + ((int64_t)iy[ty] * p.pw) * p.q_stride + o;
-      const float r = __ldg(row + ix[0] * p.q_stride) * wx[0] + __ldg(row + ix[1] * p.q_stride) * wx[1] +
-                      __ldg(row + ix[2] * p.q_stride) * wx[2] + __ldg(row + ix[3] * p.q_stride) * wx[3];
-      mine = fmaf(r, wy[ty], mine);
+      const double* row = dots_view + ((int64_t)iy[ty] * p.pw) * p.q_stride + o;
+      double r = __ldg(row + ix[0] * p.q_stride) * wx[0];
+      r = fma(__ldg(row + ix[1] * p.q_stride), wx[1], r);
+      r = fma(__ldg(row + ix[2] * p.q_stride), wx[2], r);
+      r = fma(__ldg(row + ix[3] * p.q_stride), wx[3], r);
+      mine = fma(r, wy[ty], mine);
     }
   }
   return mine;
 }
 
 template <typename More>
-__device__ __forceinline__ float finish_weight(const PixParams& p, float first, float nrm, int id, int n_q, int lane, More&& more) {
-  float pos = 0.f, red = (p.sim_kernel == DC_SIM_MAX) ? -INFINITY : 0.f;
+__device__ __forceinline__ float finish_weight(const PixParams& p, double first, float nrm, int id, int n_q, int lane, More&& more) {
+  double pos = 0.0, red = (p.sim_kernel == DC_SIM_MAX) ? -INFINITY : 0.0;
   bool nan_seen = false;
   for (int o0 = 0; o0 < n_q; o0 += 32) {
     const int o = o0 + lane;
-    float mine = o0 == 0 ? first : more(o);
-    if (p.norm_feat) mine = mine / nrm;
+    const double mine = o0 == 0 ? first : more(o);
     if (id >= o0 && id < o0 + 32) pos = __shfl_sync(0xffffffffu, mine, id - o0);
     const bool is_neg = o < n_q && o != id;
     nan_seen |= __any_sync(0xffffffffu, is_neg && (mine != mine));
-    if (p.sim_kernel == DC_SIM_MAX) red = fmaxf(red, dc::warp_max(is_neg ? mine : -INFINITY));
-    else red += dc::warp_sum(is_neg ? mine : 0.f);
+    if (p.sim_kernel == DC_SIM_MAX) red = fmax(red, warp_max_d(is_neg ? mine : -INFINITY));
+    else red += warp_sum_d(is_neg ? mine : 0.0);
   }
-  if (p.sim_kernel == DC_SIM_MEAN) red = red / (float)(n_q - 1);
-  if (nan_seen) red = __int_as_float(0x7fc00000);
-  float weight = pos - red;
+  if (p.sim_kernel == DC_SIM_MEAN) red = red / (double)(n_q - 1);
+  if (nan_seen) red = __longlong_as_double(0x7ff8000000000000ll);
+  double w = pos - red;
+  if (p.norm_feat) w = w / (double)nrm;  // nrm = 0 (an all-zero feature): 0 / 0 = NaN like the reference's f / |f|
+  float weight = (float)w;
   if (weight == weight) weight = fmaxf(weight, 1e-6f);
   return weight;
 }
@@ -179,7 +229,6 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_kernel(PixParams p) {
   const int lane = threadIdx.x & 31;
   const int per_lane = p.dim / 32;  // host guarantees dim % 32 == 0, dim <= 1024
   const int n_q = p.sim_kernel != DC_SIM_NONE ? (int)(p.query_off[scene + 1] - p.query_off[scene]) : 0;
-  const float scale_y = (float)p.ph / (float)p.height, scale_x = (float)p.pw / (float)p.width;
   const int64_t hw = (int64_t)p.height * p.width;
   const uint8_t* vis_scene = p.visible + p.mask_off[scene];
   float* w_scene = p.out_weight ? p.out_weight + p.mask_off[scene] : nullptr;
@@ -214,11 +263,13 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_kernel(PixParams p) {
       }
       int iy[4], ix[4];
       float wy[4], wx[4];
-      cubic_taps(pv, scale_y, p.ph, iy, wy);
-      cubic_taps(pu, scale_x, p.pw, ix, wx);
+      double wy64[4], wx64[4];
+      cubic_taps_exact(pv, p.ph, p.height, iy, wy, wy64);
+      cubic_taps_exact(pu, p.pw, p.width, ix, wx, wx64);
       const float* pm = p.patch + (v0 + v) * (int64_t)p.ph * p.pw * p.dim;
-      const float* dots_view = p.dots + (v0 + v) * (int64_t)p.ph * p.pw * p.q_stride;
-      const float first_dot = p.sim_kernel != DC_SIM_NONE ? interp_dot(p, dots_view, iy, ix, wy, wx, lane, n_q) : 0.f;
+      const double* dots_view = p.dots + (v0 + v) * (int64_t)p.ph * p.pw * p.q_stride;
+      auto sim_dot = [&](int o) { return interp_dot(p, dots_view, iy, ix, wy64, wx64, o, n_q); };
+      const double first_dot = p.sim_kernel != DC_SIM_NONE ? sim_dot(lane) : 0.0;
       float f[kMaxPerLane];
 #pragma unroll
       for (int k = 0; k < kMaxPerLane; ++k) f[k] = 0.f;
@@ -255,7 +306,7 @@ __global__ void __launch_bounds__(kThreads) pixel_fuse_kernel(PixParams p) {
         const int id = seg_at(p.seg, p.seg_dtype, (v0 + v) * hw + (int64_t)pv * p.width + pu);
         weight = 0.f;  // pixels whose id has no query keep metric 0 (quirk q13)
         if (id >= 0 && id < n_q)
-          weight = finish_weight(p, first_dot, nrm, id, n_q, lane, [&](int o) { return interp_dot(p, dots_view, iy, ix, wy, wx, o, n_q); });
+          weight = finish_weight(p, first_dot, nrm, id, n_q, lane, sim_dot);
         if (w_scene && lane == 0) w_scene[(int64_t)v * n_pts + i] = weight;
 #pragma unroll
         for (int k = 0; k < kMaxPerLane; ++k)
@@ -305,13 +356,16 @@ __global__ void __launch_bounds__(kThreads, 2) pixel_fuse_tile_kernel(PixParams 
   if (threadIdx.x < 9) s_K[threadIdx.x] = __ldg(p.intrinsics + (int64_t)scene * 9 + threadIdx.x);
   float4* s_acc = reinterpret_cast<float4*>(s_cam + (((size_t)n_views * 12 + 9 + 1) & ~(size_t)1));  // 16-byte aligned
   float* s_den = reinterpret_cast<float*>(s_acc + kTilePts * (kDim / 4));  // [kTilePts] denominators of fuse_points :266-268
+  // per slot and view: the 8 exact (fp64) bicubic weights (y taps, x taps) and the first tap indices, written by the
+  // lane that owns the slot, read by the warp that processes the pair
+  double* s_tw = reinterpret_cast<double*>(s_den + kTilePts);  // [kTilePts][8]
+  int* s_ti = reinterpret_cast<int*>(s_tw + kTilePts * 8);     // [kTilePts][2]
   for (int i = threadIdx.x; i < kTilePts * (kDim / 4); i += kThreads) s_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (threadIdx.x < kTilePts) s_den[threadIdx.x] = 0.f;
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_q = p.sim_kernel != DC_SIM_NONE ? (int)(p.query_off[scene + 1] - p.query_off[scene]) : 0;
-  const float scale_y = (float)p.ph / (float)p.height, scale_x = (float)p.pw / (float)p.width;
   const int64_t hw = (int64_t)p.height * p.width;
   const uint8_t* vis_scene = p.visible + p.mask_off[scene];
   float* w_scene = p.out_weight ? p.out_weight + p.mask_off[scene] : nullptr;
@@ -325,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 2) pixel_fuse_tile_kernel(PixParams 
     if (m == 0) continue;
     const int n_vis = __popc(m);
     const float4* pm = reinterpret_cast<const float4*>(p.patch + (v0 + v) * (int64_t)p.ph * p.pw * kDim);
-    const float* dots_view = p.dots + (v0 + v) * (int64_t)p.ph * p.pw * p.q_stride;
+    const double* dots_view = p.dots + (v0 + v) * (int64_t)p.ph * p.pw * p.q_stride;
     // lane-parallel projection: every lane projects ITS slot's point once per view (the same fp64 arithmetic as
     // visibility.cu; the point is visible, so it is inside); the pair loop below fetches pixels by shuffle
     const double* cam = s_cam + v * 12;
@@ -343,6 +397,19 @@ __global__ void __launch_bounds__(kThreads, 2) pixel_fuse_tile_kernel(PixParams 
         my_pu = (int)__ddiv_rn(qx, qz);
         my_pv = (int)__ddiv_rn(qy, qz);
       }
+      // every warp computes and writes the same values (m, the pixels and hence these are identical in all warps);
+      // the __syncthreads() that ends the previous visible view orders them against that view's readers
+      if (vis) {
+        double wy64[4], wx64[4];
+        s_ti[2 * lane] = cubic_weights64(my_pv, p.ph, p.height, wy64);
+        s_ti[2 * lane + 1] = cubic_weights64(my_pu, p.pw, p.width, wx64);
+#pragma unroll
+        for (int t4 = 0; t4 < 4; ++t4) {
+          s_tw[8 * lane + t4] = wy64[t4];
+          s_tw[8 * lane + 4 + t4] = wx64[t4];
+        }
+      }
+      __syncwarp();
     }
     for (int k = warp; k < n_vis; k += kWarps) {
       const int slot = __fns(m, 0, k + 1);
@@ -350,12 +417,30 @@ __global__ void __launch_bounds__(kThreads, 2) pixel_fuse_tile_kernel(PixParams 
       const int pu = __shfl_sync(0xffffffffu, my_pu, slot), pv = __shfl_sync(0xffffffffu, my_pv, slot);
       int iy[4], ix[4];
       float wy[4], wx[4];
-      cubic_taps(pv, scale_y, p.ph, iy, wy);
-      cubic_taps(pu, scale_x, p.pw, ix, wx);
+      {
+        const int iy0 = s_ti[2 * slot], ix0 = s_ti[2 * slot + 1];
+#pragma unroll
+        for (int t4 = 0; t4 < 4; ++t4) {
+          iy[t4] = min(max(iy0 - 1 + t4, 0), p.ph - 1);
+          ix[t4] = min(max(ix0 - 1 + t4, 0), p.pw - 1);
+          wy[t4] = (float)s_tw[8 * slot + t4];
+          wx[t4] = (float)s_tw[8 * slot + 4 + t4];
+        }
+      }
       // the instance id and the first round of query dots are requested before the taps: both are cold loads whose
       // latency then hides behind the 96 tap loads instead of sitting in front of the accumulator update
       long long raw_id = p.sim_kernel != DC_SIM_NONE ? seg_raw(p.seg, p.seg_dtype, (v0 + v) * hw + (int64_t)pv * p.width + pu) : -1;
-      const float first_dot = p.sim_kernel != DC_SIM_NONE ? interp_dot(p, dots_view, iy, ix, wy, wx, lane, n_q) : 0.f;
+      // the fp64 weights are re-read from shared memory inside the lambda (broadcast loads; nothing stays live)
+      auto sim_dot = [&](int o) {
+        double wy64[4], wx64[4];
+#pragma unroll
+        for (int t4 = 0; t4 < 4; ++t4) {
+          wy64[t4] = s_tw[8 * slot + t4];
+          wx64[t4] = s_tw[8 * slot + 4 + t4];
+        }
+        return interp_dot(p, dots_view, iy, ix, wy64, wx64, o, n_q);
+      };
+      const double first_dot = p.sim_kernel != DC_SIM_NONE ? sim_dot(lane) : 0.0;
       // Chunk-major: the 16 taps of one 128-channel chunk are requested back to back (16 independent 128-bit loads
       // in flight per lane) and folded in the ATen order (along x inside each row, then along y); finished chunks
       // occupy 4 registers each, so the loads of the next chunk have room without spilling.
@@ -416,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, 2) pixel_fuse_tile_kernel(PixParams 
         const int id = seg_id(raw_id);
         float weight = 0.f;  // pixels whose id has no query keep metric 0 (quirk q13)
         if (id >= 0 && id < n_q)
-          weight = finish_weight(p, first_dot, nrm, id, n_q, lane, [&](int o) { return interp_dot(p, dots_view, iy, ix, wy, wx, o, n_q); });
+          weight = finish_weight(p, first_dot, nrm, id, n_q, lane, sim_dot);
         if (w_scene && lane == 0) w_scene[(int64_t)v * n_pts + i] = weight;
         if (lane == 0) s_den[slot] += weight;
 #pragma unroll
@@ -572,7 +657,7 @@ unsigned blocks_for(int64_t max_points, int n_scenes) {
   return (unsigned)(want < 1 ? 1 : want);
 }
 
-int query_stride(int max_queries) { return (max_queries + 7) & ~7; }  // whole 32-byte sectors per (cell) row
+int query_stride(int max_queries) { return (max_queries + 3) & ~3; }  // whole 32-byte sectors per (cell) row of doubles
 
 }  // namespace
 
@@ -580,7 +665,7 @@ extern "C" {
 
 size_t dc_pixel_fuse_workspace(int64_t total_views, int patch_h, int patch_w, int max_queries_per_scene) {
   if (total_views <= 0 || patch_h <= 0 || patch_w <= 0 || max_queries_per_scene <= 0) return 0;
-  return (size_t)total_views * patch_h * patch_w * query_stride(max_queries_per_scene) * sizeof(float);
+  return (size_t)total_views * patch_h * patch_w * query_stride(max_queries_per_scene) * sizeof(double);
 }
 
 int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t* view_off, const double* inv_poses,
@@ -610,7 +695,8 @@ int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t*
     DC_CHECK_ARG(total_views >= 0 && max_queries_per_scene >= 0, "dc_pixel_fuse: bad extents");
     const size_t need = dc_pixel_fuse_workspace(total_views, patch_h, patch_w, max_queries_per_scene);
     DC_CHECK_ARG(workspace && workspace_bytes >= need, "dc_pixel_fuse: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
-    p.dots = static_cast<float*>(workspace);
+    DC_CHECK_ARG(((uintptr_t)workspace & 7) == 0, "dc_pixel_fuse: workspace must be 8-byte aligned");
+    p.dots = static_cast<double*>(workspace);
     p.q_stride = query_stride(max_queries_per_scene);
     if (total_views > 0 && max_queries_per_scene > 0) {
       const int64_t rows = (int64_t)max_views_per_scene * patch_h * patch_w;
@@ -621,7 +707,8 @@ int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t*
   }
   if (aligned && (dim == 768 || dim == 512 || dim == 1024)) {  // CLIP ViT-L/14, ViT-B, ViT-H widths
     const size_t cam_doubles = ((size_t)max_views_per_scene * 12 + 9 + 1) & ~(size_t)1;
-    const size_t tsmem = cam_doubles * sizeof(double) + (size_t)kTilePts * dim * sizeof(float) + kTilePts * sizeof(float);
+    const size_t tsmem = cam_doubles * sizeof(double) + (size_t)kTilePts * dim * sizeof(float) + kTilePts * sizeof(float) +
+                         kTilePts * (8 * sizeof(double) + 2 * sizeof(int));
     dim3 tgrid((unsigned)dc::ceil_div<int64_t>(max_points_per_scene, kTilePts), (unsigned)n_scenes);
     DC_CHECK_ARG(tsmem <= 200 * 1024, "dc_pixel_fuse: too many views per scene (%d)", max_views_per_scene);
     // the attribute belongs to the (function, device) pair, so it is set on every call for the device in use

@@ -80,11 +80,11 @@ def visibility_mask(points, depths, poses, K, height, width, threshold=0.05, dev
     return out
 
 
-def relative_similarity(pos, neg, method: str, eps: float = 1e-6):
+def relative_similarity(pos, neg, method: str, eps: float = 1e-6, work=torch.float32):
     if method == "max":
-        return torch.clip(pos - torch.max(neg, dim=-1)[0], eps).squeeze().float()
+        return torch.clip(pos - torch.max(neg, dim=-1)[0], eps).squeeze().to(work)
     if method == "mean":
-        return torch.clip(pos - neg.mean(-1), eps).squeeze().float()
+        return torch.clip(pos - neg.mean(-1), eps).squeeze().to(work)
     raise ValueError("Please set method in [mean, max]")
 
 
@@ -133,24 +133,30 @@ def fuse_object_level(points, colors, labels, depths, seg_masks, poses, mv_featu
 
 def aggregate_pixel_level(points, depths, seg_masks, poses, mv_features, query, K, height, width,
                           feature_size=768, threshold=0.05, use_similarity=True, sim_method="max",
-                          norm_feat=True, device="cpu"):
+                          norm_feat=True, device="cpu", work=torch.float32):
+    """`work=torch.float32` is the reference's arithmetic. `work=torch.float64` evaluates the SAME formulas in
+    double precision (features and queries widened first): the tests use it as the exact value when they
+    measure how far the reference's own fp32 roundings are from it."""
     n, n_views = points.shape[0], len(depths)
     vis = torch.zeros((n_views, n), dtype=torch.long, device=device)
-    simw = torch.zeros((n_views, n), dtype=torch.float32, device=device) if use_similarity else None
-    acc = torch.zeros((n, feature_size), dtype=torch.float32, device=device)
+    simw = torch.zeros((n_views, n), dtype=work, device=device) if use_similarity else None
+    acc = torch.zeros((n, feature_size), dtype=work, device=device)
+    if work != torch.float32:
+        mv_features = [f.to(work) for f in mv_features]
+        query = query.to(work) if query is not None else None
     for v in range(n_views):
         fmap = F.interpolate(mv_features[v].permute(2, 0, 1).unsqueeze(0), size=(height, width),
                              mode="bicubic", align_corners=False).squeeze().permute(1, 2, 0)
         if norm_feat:
             fmap /= fmap.norm(dim=-1, keepdim=True)
         if use_similarity:
-            raw = fmap.float() @ query.T
-            metric = torch.zeros((height, width), dtype=torch.float32, device=device)
+            raw = fmap.to(work) @ query.T
+            metric = torch.zeros((height, width), dtype=work, device=device)
             for obj in range(len(query)):
                 region = seg_masks[v] == obj
                 sub = raw[region]
                 others = torch.as_tensor([o for o in range(len(query)) if o != obj]).long().to(device)
-                metric[region] = relative_similarity(sub[:, obj], sub[:, others], sim_method)
+                metric[region] = relative_similarity(sub[:, obj], sub[:, others], sim_method, work=work)
         pix, zd = project_to_pixels(points, poses[v], K)
         inside, cols = view_visibility(pix, zd, depths[v], height, width, threshold, device)
         vis[v] = inside
