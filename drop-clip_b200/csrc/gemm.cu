@@ -52,9 +52,24 @@ using dc::gemm::Tile;
 
 // ---------------------------------------------------------------------------- row normalisation
 // One warp per row. torch semantics per dtype:
-//   fp16: norm = fp16(sqrt(sum_fp32 x^2)); y = fp16(float(x) / float(norm))       (rounded twice)
-//   fp32: norm = sqrt(sum_fp32 x^2);       y = x / norm
+//   fp16: norm = fp16(sqrt(sum x^2)); y = fp16(float(x) / float(norm))       (rounded twice)
+//   fp32: norm = sqrt(sum x^2);       y = x / norm
+// The sum of squares is accumulated in fp64, so the norm is the CORRECTLY ROUNDED one. torch accumulates in fp32
+// in an order that depends on the kernel (CPU vector width / CUDA block shape); its fp16 norm then lands on the
+// neighbouring fp16 value whenever the exact norm sits within ~1e-7 of a rounding boundary - 3.5 rows in 10 000
+// (measured: 70 of 200 000 random 768-d rows), and such a flip moves every similarity of the row by 5e-4. No fp32
+// order can follow all of torch's builds; the exactly rounded norm is the value they all approximate.
 // Writes y back in place when `normalize`, and the fp16 operand planes when requested.
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ float rounded_norm(double sum_sq) {
+  const double nrm = sqrt(sum_sq);
+  return sizeof(T) == 2 ? __half2float(__double2half(nrm)) : (float)nrm;
+}
 template <typename T, bool kInPlace>
 __global__ void __launch_bounds__(256) row_normalize_kernel(T* __restrict__ x, int64_t n_rows, int dim, int normalize,
                                                             __half* __restrict__ hi, __half* __restrict__ lo) {
@@ -64,15 +79,12 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(T* __restrict__ x, i
   T* xr = x + row * dim;
   float inv_scale_num = 1.f;  // divide by this
   if (normalize) {
-    float ss = 0.f;
+    double ss = 0.0;
     for (int c = lane; c < dim; c += 32) {
-      const float v = (float)xr[c];
-      ss = fmaf(v, v, ss);
+      const double v = (double)(float)xr[c];
+      ss = fma(v, v, ss);
     }
-    ss = dc::warp_sum(ss);
-    float nrm = sqrtf(ss);
-    if (sizeof(T) == 2) nrm = __half2float(__float2half_rn(nrm));
-    inv_scale_num = nrm;
+    inv_scale_num = rounded_norm<T>(warp_sum_f64(ss));
   }
   for (int c = lane; c < dim; c += 32) {
     float v = (float)xr[c];
@@ -121,14 +133,12 @@ __global__ void __launch_bounds__(256) row_normalize_vec_kernel(T* __restrict__ 
     }
   }
   if (normalize) {
-    float ss = 0.f;
+    double ss = 0.0;
 #pragma unroll
     for (int k = 0; k < kChunks; ++k)
 #pragma unroll
-      for (int j = 0; j < kPer; ++j) ss = fmaf(v[k][j], v[k][j], ss);
-    ss = dc::warp_sum(ss);
-    float nrm = sqrtf(ss);
-    if (sizeof(T) == 2) nrm = __half2float(__float2half_rn(nrm));
+      for (int j = 0; j < kPer; ++j) ss = fma((double)v[k][j], (double)v[k][j], ss);
+    const float nrm = rounded_norm<T>(warp_sum_f64(ss));
 #pragma unroll
     for (int k = 0; k < kChunks; ++k)
 #pragma unroll
@@ -404,7 +414,7 @@ __global__ void __launch_bounds__(128) view_weights_kernel(
     const float* __restrict__ sims, int sims_ld, const int64_t* __restrict__ feat_off, const int32_t* __restrict__ view_scene,
     const int64_t* __restrict__ view_off, const int64_t* __restrict__ query_off, const int64_t* __restrict__ wobj_off,
     const int32_t* __restrict__ row_object, const uint32_t* __restrict__ counts, int nbins, int64_t total_views,
-    int sim_kernel, int use_visibility, float* __restrict__ weight_obj) {
+    int sim_kernel, int use_visibility, float* __restrict__ weight_obj, float* __restrict__ view_minmax) {
   const int64_t g = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (g >= total_views) return;
   const int lane = threadIdx.x & 31;
@@ -428,6 +438,10 @@ __global__ void __launch_bounds__(128) view_weights_kernel(
     mx = dc::warp_max(mx);
     any_nan = __any_sync(0xffffffffu, any_nan);
     if (any_nan) mn = mx = __int_as_float(0x7fc00000);  // torch min()/max() propagate NaN
+    if (view_minmax && lane == 0) {
+      view_minmax[2 * g] = mn;
+      view_minmax[2 * g + 1] = mx;
+    }
   }
   const float range = mx - mn;
   for (int64_t r = r0 + lane; r < r1; r += 32) {
@@ -455,6 +469,92 @@ __global__ void __launch_bounds__(128) view_weights_kernel(
     }
     w_scene[(int64_t)obj * n_v + v_local] = w;
   }
+}
+
+// Exact similarity weights (second pass, one warp per feature row). The weight clip(pos - max|mean(neg), 1e-6) of
+// the min-max normalised similarities equals (s_pos - red(s_neg)) / (max - min): the view's minimum cancels, the range
+// only scales. What needs precision is the DIFFERENCE of two cosines ~1: the tensor-core GEMM (and the reference's own
+// fp32 sgemm) carry ~1e-7 of absolute noise, which is a relative error of 10 % on a weight next to the 1e-6 clip, and
+// the fused feature of an object whose views all score that low is a mean under such weights (measured at V = 73:
+// 3e-3 off the reference on one object row, the reference itself being that far from the exact value of its own
+// formulas). So the GEMM's similarities only SELECT here: the positive and every negative within `tol` of the
+// arg-max (all negatives for the mean kernel) are re-evaluated as fp64 dot products of the normalised feature row
+// (normalised the way torch does per dtype, like row_normalize_kernel) with the queries, and the weight is formed in
+// fp64 and rounded once.
+template <typename T>
+__global__ void __launch_bounds__(256) refine_weights_kernel(
+    const T* __restrict__ feats, int dim, const float* __restrict__ queries, const float* __restrict__ sims, int sims_ld,
+    const int64_t* __restrict__ feat_off, const int32_t* __restrict__ view_scene, const int64_t* __restrict__ view_off,
+    const int64_t* __restrict__ query_off, const int64_t* __restrict__ wobj_off, const int32_t* __restrict__ row_object,
+    const float* __restrict__ view_minmax, int64_t total_views, int64_t total_rows, int sim_kernel,
+    float* __restrict__ weight_obj) {
+  constexpr int kMaxPerLane = 32;  // dim <= 1024
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= total_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int obj = row_object[r];
+  if (obj < 0) return;
+  // view of this row: last g with feat_off[g] <= r
+  int64_t lo = 0, hi = total_views - 1;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) >> 1;
+    if (__ldg(feat_off + mid) <= r) lo = mid; else hi = mid - 1;
+  }
+  const int64_t g = lo;
+  const int s = view_scene[g];
+  const int n_q = (int)(query_off[s + 1] - query_off[s]);
+  const int n_v = (int)(view_off[s + 1] - view_off[s]);
+  const int v_local = (int)(g - view_off[s]);
+  const float mn = view_minmax[2 * g], mx = view_minmax[2 * g + 1];
+  const float* srow = sims + r * sims_ld;
+  // normalised row in registers (fp32 holds the fp16-rounded quotients exactly)
+  const T* x = feats + r * dim;
+  float y[kMaxPerLane];
+  {
+    double ss = 0.0;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+      y[k] = (k * 32 + lane < dim) ? (float)x[k * 32 + lane] : 0.f;
+      ss = fma((double)y[k], (double)y[k], ss);
+    }
+    const float nrm = rounded_norm<T>(warp_sum_f64(ss));  // same rule as row_normalize_kernel
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+      const float q = y[k] / nrm;  // IEEE division, like torch
+      y[k] = sizeof(T) == 2 ? __half2float(__float2half_rn(q)) : q;
+    }
+  }
+  // approximate arg-max of the negatives (fp32 similarities of the GEMM) and the selection tolerance
+  float neg_max = -INFINITY;
+  for (int o = 0; o < n_q; ++o)
+    if (o != obj) neg_max = fmaxf(neg_max, srow[o]);
+  const float tol = 1e-5f * fmaxf(fmaxf(fabsf(mn), fabsf(mx)), 1e-30f);
+  const float* q0 = queries + query_off[s] * (int64_t)dim;
+  double pos = 0.0, red = (sim_kernel == DC_SIM_MAX) ? -INFINITY : 0.0;
+  bool nan_seen = false;
+  for (int o = 0; o < n_q; ++o) {
+    const float so = srow[o];
+    const bool take = (o == obj) || (sim_kernel == DC_SIM_MEAN) || !(so < neg_max - tol);  // NaN similarities are taken
+    if (!take) continue;  // warp-uniform
+    const float* q = q0 + (int64_t)o * dim;
+    double d = 0.0;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k)
+      if (k * 32 + lane < dim) d = fma((double)y[k], (double)__ldg(q + k * 32 + lane), d);
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sh);
+    if (o == obj) pos = d;
+    else {
+      nan_seen |= (d != d);
+      if (sim_kernel == DC_SIM_MAX) red = fmax(red, d);
+      else red += d;
+    }
+  }
+  if (sim_kernel == DC_SIM_MEAN) red = red / (double)(n_q - 1);
+  if (nan_seen) red = __longlong_as_double(0x7ff8000000000000ll);
+  float w = (float)((pos - red) / ((double)mx - (double)mn));  // NaN extrema (a NaN anywhere in the view) give NaN, like torch
+  if (w == w) w = fmaxf(w, 1e-6f);
+  if (lane == 0) weight_obj[wobj_off[s] + (int64_t)obj * n_v + v_local] = w;
 }
 
 __global__ void init_minmax_kernel(float* m) {
@@ -562,17 +662,34 @@ int dc_view_score(const void* feats, int feat_dtype, int64_t total_rows, int dim
 int dc_view_weights(const float* sims, int sims_ld, const int64_t* feat_off, const int32_t* view_scene,
                     const int64_t* view_off, const int64_t* query_off, const int64_t* wobj_off,
                     const int32_t* row_object, const uint32_t* counts, int nbins, int64_t total_views,
-                    int sim_kernel, int use_visibility, float* weight_obj, dc_stream_t stream) {
+                    int sim_kernel, int use_visibility, float* weight_obj, const void* feats, int feat_dtype, int dim,
+                    const float* queries, int64_t total_rows, float* view_minmax, dc_stream_t stream) {
   DC_CHECK_ARG(feat_off && view_scene && view_off && query_off && wobj_off && row_object && weight_obj,
                "dc_view_weights: null pointer argument");
   DC_CHECK_ARG(sim_kernel == DC_SIM_NONE || sims, "dc_view_weights: sims required for a similarity kernel");
   DC_CHECK_ARG(!use_visibility || counts, "dc_view_weights: counts required for use_visibility");
   DC_CHECK_ARG(sim_kernel >= DC_SIM_NONE && sim_kernel <= DC_SIM_MEAN, "dc_view_weights: Please set method in [mean, max]");
+  const bool refine = feats && sim_kernel != DC_SIM_NONE;
+  DC_CHECK_ARG(!refine || (queries && view_minmax && dim > 0 && dim <= 1024 && (feat_dtype == DC_F16 || feat_dtype == DC_F32)),
+               "dc_view_weights: exact weights need queries, view_minmax and fp16/fp32 features of dim <= 1024");
   if (total_views <= 0) return DC_OK;
-  view_weights_kernel<<<(unsigned)dc::ceil_div<int64_t>(total_views, 4), 128, 0, dc::as_stream(stream)>>>(
+  cudaStream_t st = dc::as_stream(stream);
+  view_weights_kernel<<<(unsigned)dc::ceil_div<int64_t>(total_views, 4), 128, 0, st>>>(
       sims, sims_ld, feat_off, view_scene, view_off, query_off, wobj_off, row_object, counts, nbins, total_views,
-      sim_kernel, use_visibility, weight_obj);
+      sim_kernel, use_visibility, weight_obj, refine ? view_minmax : nullptr);
   DC_LAUNCH_CHECK();
+  if (refine && total_rows > 0) {
+    const unsigned grid = (unsigned)dc::ceil_div<int64_t>(total_rows, 8);
+    if (feat_dtype == DC_F16)
+      refine_weights_kernel<__half><<<grid, 256, 0, st>>>((const __half*)feats, dim, queries, sims, sims_ld, feat_off, view_scene,
+                                                         view_off, query_off, wobj_off, row_object, view_minmax, total_views,
+                                                         total_rows, sim_kernel, weight_obj);
+    else
+      refine_weights_kernel<float><<<grid, 256, 0, st>>>((const float*)feats, dim, queries, sims, sims_ld, feat_off, view_scene,
+                                                        view_off, query_off, wobj_off, row_object, view_minmax, total_views,
+                                                        total_rows, sim_kernel, weight_obj);
+    DC_LAUNCH_CHECK();
+  }
   return DC_OK;
 }
 

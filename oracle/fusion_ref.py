@@ -99,21 +99,30 @@ def broadcast_object_feats(n_points: int, labels: np.ndarray, feat: torch.Tensor
 
 def fuse_object_level(points, colors, labels, depths, seg_masks, poses, mv_features, query, K, height, width,
                       threshold=0.05, use_visibility=False, use_similarity=True, sim_method="max",
-                      return_obj=False, device="cpu"):
+                      return_obj=False, device="cpu", work=torch.float32):
+    """`work=torch.float32` is the reference's arithmetic. `work=torch.float64` evaluates the SAME formulas in
+    double precision from the point where the reference goes to fp32 (`feat_v_norm.float() @ query.T`, :312: the
+    normalised rows keep the feature dtype's own roundings, then everything is widened): the exact value the tests
+    measure the reference's fp32 rounding noise against."""
     vis = visibility_mask(points, depths, poses, K, height, width, threshold, device)
     seen = (vis.sum(0) > 0).cpu().numpy()
     points, colors, labels = points[seen], colors[seen], labels[seen]
     vis = vis[:, seen]
 
     n_obj, n_views = query.shape[0], len(mv_features)
-    stacked = torch.zeros((n_obj, n_views, 768), dtype=torch.float32, device=device)
-    weight = torch.zeros((n_obj, n_views), dtype=torch.float32, device=device)
+    stacked = torch.zeros((n_obj, n_views, 768), dtype=work, device=device)
+    weight = torch.zeros((n_obj, n_views), dtype=work, device=device)
     for v in range(n_views):
         feat_v, seg = mv_features[v], seg_masks[v]
         ids = np.unique(seg)[1:].tolist()
         if use_similarity:
-            unit = feat_v / feat_v.norm(dim=-1, keepdim=True)
-            sim = unit.float() @ query.T
+            if work == torch.float32:
+                unit = feat_v / feat_v.norm(dim=-1, keepdim=True)
+            else:
+                # the correctly rounded norm: torch's fp32-accumulated norm of an fp16 row lands on the neighbouring
+                # fp16 value for ~3.5 rows in 10 000 (whenever the exact norm is within 1e-7 of a rounding boundary)
+                unit = feat_v / feat_v.double().norm(dim=-1, keepdim=True).to(feat_v.dtype)
+            sim = unit.to(work) @ query.to(work).T
             sim = (sim - sim.min()) / (sim.max() - sim.min())
         for i, obj in enumerate(ids):
             weight[obj, v] = 1.0
@@ -121,7 +130,7 @@ def fuse_object_level(points, colors, labels, depths, seg_masks, poses, mv_featu
                 weight[obj, v] = float((seg == obj).sum())
             if use_similarity:
                 others = torch.as_tensor([o for o in range(n_obj) if o != obj]).long().to(device)
-                weight[obj, v] = relative_similarity(sim[i][obj], sim[i][others], sim_method).item()
+                weight[obj, v] = relative_similarity(sim[i][obj], sim[i][others], sim_method, work=work).item()
             stacked[obj, v] = feat_v[i]
     fused = torch.einsum("kvc,kv->kc", stacked, weight) / weight.sum(1).unsqueeze(-1)
     if not return_obj:

@@ -77,12 +77,19 @@ def test_full_scene_object_fusion_vs_oracle(obj_case):
     from oracle import fusion_ref
     sc = obj_case["sc"]
     K = fusion_ref.intrinsic_matrix(sc.intrinsic)
-    (of, ow, ov), (op, oc, ol) = fusion_ref.fuse_object_level(
-        sc.points, sc.colors, sc.labels, sc.depths, sc.seg_masks, sc.camera_poses, sc.mv_features, sc.query_embeddings, K,
-        480, 640, use_visibility=False, use_similarity=True, sim_method="max", return_obj=True)
+    args = (sc.points, sc.colors, sc.labels, sc.depths, sc.seg_masks, sc.camera_poses, sc.mv_features, sc.query_embeddings, K,
+            480, 640)
+    (of, ow, ov), (op, oc, ol) = fusion_ref.fuse_object_level(*args, use_visibility=False, use_similarity=True, sim_method="max",
+                                                              return_obj=True)
     assert np.array_equal(obj_case["vis"].numpy(), ov.numpy()) and np.array_equal(obj_case["p"], op)
-    rel_close(obj_case["w"], ow.numpy(), what="full-size weight_obj")
-    rel_close(obj_case["feat"], of.numpy(), what="full-size object features")
+    # weights next to the 1e-6 clip carry the fp32 GEMM's absolute noise as a LARGE relative error in the reference
+    # itself; exact_close bounds the CUDA path against the fp64 evaluation of the same formulas and against the fp32
+    # one up to the distance that fp32 evaluation keeps from the exact value (no element excluded)
+    (xf, xw, _), _ = fusion_ref.fuse_object_level(*args, use_visibility=False, use_similarity=True, sim_method="max",
+                                                  return_obj=True, work=torch.float64)
+    exact_close(obj_case["w"], ow.numpy(), xw.numpy(), what="full-size weight_obj")
+    exact_close(obj_case["feat"], of.numpy(), xf.numpy(), what="full-size object features")
+    obj_case["exact"] = (xf.numpy(), xw.numpy())
     assert np.isnan(of.numpy()[0]).all(), "the table row is seen in no view: NaN (quirk q10)"
 
 
@@ -100,15 +107,26 @@ def test_full_scene_object_fusion_vs_reference_golden(obj_case):
     assert sha(obj_case["c"]) == str(z["kept_colors_sha"]) and sha(obj_case["l"]) == str(z["kept_labels_sha"])
     full = obj_case["M"].get_visibility_mask(sc.points, sc.depths, sc.camera_poses, device="cuda").numpy().astype(np.uint8)
     assert sha(full) == str(z["vis_full_sha"]), "(V, N) visibility mask differs from the reference's"
-    rel_close(obj_case["w"], z["weight"], what="weight_obj vs reference")
-    rel_close(obj_case["feat"], z["feat"], what="object features vs reference")
+    if "exact" not in obj_case:
+        from oracle import fusion_ref
+        (xf, xw, _), _ = fusion_ref.fuse_object_level(
+            sc.points, sc.colors, sc.labels, sc.depths, sc.seg_masks, sc.camera_poses, sc.mv_features, sc.query_embeddings,
+            fusion_ref.intrinsic_matrix(sc.intrinsic), 480, 640, use_visibility=False, use_similarity=True, sim_method="max",
+            return_obj=True, work=torch.float64)
+        obj_case["exact"] = (xf.numpy(), xw.numpy())
+    xf, xw = obj_case["exact"]
+    exact_close(obj_case["w"], z["weight"], xw, what="weight_obj vs reference")
+    exact_close(obj_case["feat"], z["feat"], xf, what="object features vs reference")
     # return_obj=False: per-point rows are copies of the object rows (or zeros); sampled rows of the reference's result
     (pf, _, _), _ = obj_case["M"].fuse(sc.points, sc.colors, sc.labels, sc.depths, sc.seg_masks, sc.camera_poses,
                                        sc.mv_features, sc.query_embeddings, return_obj=False, device="cuda")
     assert pf.device.type == "cpu" and pf.shape == (int(z["n_kept"][0]), 768)
     rows = np.sort(np.random.default_rng(7).choice(pf.shape[0], size=z["point_feat_rows"].shape[0], replace=False))
-    rel_close(pf.numpy()[rows], z["point_feat_rows"], what="per-point features vs reference")
     lab = obj_case["l"]
+    exact_rows = np.zeros((rows.size, 768))
+    for o in range(1, 21):
+        exact_rows[lab[rows] == o] = xf[o]
+    exact_close(pf.numpy()[rows], z["point_feat_rows"], exact_rows, what="per-point features vs reference")
     got = pf.numpy()
     want = np.zeros_like(got)
     for o in range(1, 21):
