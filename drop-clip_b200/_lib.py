@@ -36,7 +36,9 @@ SIGNATURES = {
     "dc_view_score_ld": (c_int, [c_int]),
     "dc_view_score_workspace": (c_size_t, [c_int64, c_int64, c_int, c_int]),
     "dc_view_score": (c_int, [P, c_int, c_int64, c_int, P, P, P, P, c_int64, c_int, c_int, P, c_int, P, c_size_t, P]),
-    "dc_view_weights": (c_int, [P, c_int, P, P, P, P, P, P, P, c_int, c_int64, c_int, c_int, P, P, c_int, c_int, P, c_int64, P, P]),
+    "dc_view_weights_scratch": (c_size_t, [c_int64, c_int64]),
+    "dc_view_weights": (c_int, [P, c_int, P, P, P, P, P, P, P, c_int, c_int64, c_int, c_int, P, P, c_int, c_int, P, c_int64, P, P,
+                                ctypes.c_float, P]),
     "dc_segmented_wmean": (c_int, [P, c_int, c_int, P, P, P, P, P, c_int, c_int, P, P]),
     "dc_scatter_to_points": (c_int, [P, P, P, P, c_int, c_int64, c_int, c_int, P, P]),
     "dc_compact_workspace": (c_size_t, [c_int64]),

@@ -2,6 +2,7 @@
 //
 // Reference: utils/feature_fusion.py:311-313 (feat_v_norm @ query.T), models/similarity.py:28-101
 // (vis_feats @ text.T, paired softmax, min-max, threshold), engine/distil.py:244-246.
+#include <algorithm>
 #include <mutex>
 
 #include "gemm.cuh"
@@ -414,7 +415,8 @@ __global__ void __launch_bounds__(128) view_weights_kernel(
     const float* __restrict__ sims, int sims_ld, const int64_t* __restrict__ feat_off, const int32_t* __restrict__ view_scene,
     const int64_t* __restrict__ view_off, const int64_t* __restrict__ query_off, const int64_t* __restrict__ wobj_off,
     const int32_t* __restrict__ row_object, const uint32_t* __restrict__ counts, int nbins, int64_t total_views,
-    int sim_kernel, int use_visibility, float* __restrict__ weight_obj, float* __restrict__ view_minmax) {
+    int sim_kernel, int use_visibility, float* __restrict__ weight_obj, float* __restrict__ view_minmax,
+    int* __restrict__ refine_list, float refine_below) {
   const int64_t g = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (g >= total_views) return;
   const int lane = threadIdx.x & 31;
@@ -466,6 +468,12 @@ __global__ void __launch_bounds__(128) view_weights_kernel(
       w = pos - red;
       // torch.clip(x, min=eps): NaN stays NaN
       if (w == w) w = fmaxf(w, 1e-6f);
+      // rows whose weight the GEMM's ~1e-7 of absolute noise does not resolve: queued for refine_weights_kernel
+      if (refine_list && !(w >= refine_below)) {
+        const int slot = atomicAdd(refine_list, 1);
+        refine_list[1 + 2 * slot] = (int)r;
+        refine_list[2 + 2 * slot] = (int)g;
+      }
     }
     w_scene[(int64_t)obj * n_v + v_local] = w;
   }
@@ -481,80 +489,138 @@ __global__ void __launch_bounds__(128) view_weights_kernel(
 // arg-max (all negatives for the mean kernel) are re-evaluated as fp64 dot products of the normalised feature row
 // (normalised the way torch does per dtype, like row_normalize_kernel) with the queries, and the weight is formed in
 // fp64 and rounded once.
-template <typename T>
+// `normed`: the fp16 plane of normalised rows dc_view_score left in its workspace (fp16 features: exactly the values
+// the reference multiplies; then no norm and no division here) or nullptr (fp32 features: the row is normalised here
+// from `feats`). kVec: dim is a multiple of 256 and the rows are 16-byte aligned - a lane owns 8 consecutive channels
+// of every 256-channel chunk (128-bit loads). Only rows whose GEMM weight is below `refine_below` are re-evaluated
+// (view_weights_kernel queues them): the GEMM's absolute noise of ~1e-7 is a relative error below 1e-5 on a weight
+// above 0.02.
+template <typename T, bool kVec>
 __global__ void __launch_bounds__(256) refine_weights_kernel(
-    const T* __restrict__ feats, int dim, const float* __restrict__ queries, const float* __restrict__ sims, int sims_ld,
-    const int64_t* __restrict__ feat_off, const int32_t* __restrict__ view_scene, const int64_t* __restrict__ view_off,
-    const int64_t* __restrict__ query_off, const int64_t* __restrict__ wobj_off, const int32_t* __restrict__ row_object,
-    const float* __restrict__ view_minmax, int64_t total_views, int64_t total_rows, int sim_kernel,
-    float* __restrict__ weight_obj) {
+    const T* __restrict__ feats, const __half* __restrict__ normed, int dim, const float* __restrict__ queries,
+    const float* __restrict__ sims, int sims_ld, const int64_t* __restrict__ feat_off, const int32_t* __restrict__ view_scene,
+    const int64_t* __restrict__ view_off, const int64_t* __restrict__ query_off, const int64_t* __restrict__ wobj_off,
+    const int32_t* __restrict__ row_object, const float* __restrict__ view_minmax, int sim_kernel,
+    const int* __restrict__ refine_list, float* __restrict__ weight_obj) {
   constexpr int kMaxPerLane = 32;  // dim <= 1024
-  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (r >= total_rows) return;
+  // persistent warps over the (row, view) list view_weights_kernel queued
   const int lane = threadIdx.x & 31;
-  const int obj = row_object[r];
-  if (obj < 0) return;
-  // view of this row: last g with feat_off[g] <= r
-  int64_t lo = 0, hi = total_views - 1;
-  while (lo < hi) {
-    const int64_t mid = (lo + hi + 1) >> 1;
-    if (__ldg(feat_off + mid) <= r) lo = mid; else hi = mid - 1;
-  }
-  const int64_t g = lo;
-  const int s = view_scene[g];
-  const int n_q = (int)(query_off[s + 1] - query_off[s]);
-  const int n_v = (int)(view_off[s + 1] - view_off[s]);
-  const int v_local = (int)(g - view_off[s]);
-  const float mn = view_minmax[2 * g], mx = view_minmax[2 * g + 1];
-  const float* srow = sims + r * sims_ld;
-  // normalised row in registers (fp32 holds the fp16-rounded quotients exactly)
-  const T* x = feats + r * dim;
-  float y[kMaxPerLane];
-  {
-    double ss = 0.0;
+  const int n_items = refine_list[0];
+  const int n_chunks = kVec ? dim / 256 : (dim + 31) / 32;  // per-lane groups of 8 (vector) or single (scalar) channels
+  for (int item = blockIdx.x * 8 + (threadIdx.x >> 5); item < n_items; item += gridDim.x * 8) {
+    const int64_t r = refine_list[1 + 2 * item], g = refine_list[2 + 2 * item];
+    const int s = view_scene[g];
+    const int n_q = (int)(query_off[s + 1] - query_off[s]);
+    const int n_v = (int)(view_off[s + 1] - view_off[s]);
+    const int v_local = (int)(g - view_off[s]);
+    const float mn = view_minmax[2 * g], mx = view_minmax[2 * g + 1];
+    const float tol = 1e-5f * fmaxf(fmaxf(fabsf(mn), fabsf(mx)), 1e-30f);
+    const float* q0 = queries + query_off[s] * (int64_t)dim;
+    const int obj = row_object[r];
+    float* w_slot = weight_obj + wobj_off[s] + (int64_t)obj * n_v + v_local;
+    const float* srow = sims + r * sims_ld;
+    float y[kMaxPerLane];
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) {
-      y[k] = (k * 32 + lane < dim) ? (float)x[k * 32 + lane] : 0.f;
-      ss = fma((double)y[k], (double)y[k], ss);
+    for (int k = 0; k < kMaxPerLane; ++k) y[k] = 0.f;
+    if (normed) {
+      const __half* yr = normed + r * dim;
+      if (kVec) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < n_chunks) {
+            const int4 raw = __ldg(reinterpret_cast<const int4*>(yr) + k * 32 + lane);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(h2[j]);
+              y[k * 8 + 2 * j] = f.x;
+              y[k * 8 + 2 * j + 1] = f.y;
+            }
+          }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k)
+          if (k * 32 + lane < dim) y[k] = __half2float(yr[k * 32 + lane]);
+      }
+    } else {
+      const T* x = feats + r * dim;
+      double ss = 0.0;
+      if (kVec) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < n_chunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[k * 8 + j] = (float)x[(k * 32 + lane) * 8 + j];
+          }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k)
+          if (k * 32 + lane < dim) y[k] = (float)x[k * 32 + lane];
+      }
+#pragma unroll
+      for (int k = 0; k < kMaxPerLane; ++k) ss = fma((double)y[k], (double)y[k], ss);
+      const float nrm = rounded_norm<T>(warp_sum_f64(ss));  // same rule as row_normalize_kernel
+#pragma unroll
+      for (int k = 0; k < kMaxPerLane; ++k) {
+        const float q = y[k] / nrm;  // IEEE division, like torch
+        y[k] = sizeof(T) == 2 ? __half2float(__float2half_rn(q)) : q;
+      }
     }
-    const float nrm = rounded_norm<T>(warp_sum_f64(ss));  // same rule as row_normalize_kernel
-#pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) {
-      const float q = y[k] / nrm;  // IEEE division, like torch
-      y[k] = sizeof(T) == 2 ? __half2float(__float2half_rn(q)) : q;
+    // approximate arg-max of the negatives from the GEMM's fp32 similarities (lane o holds query o0 + o)
+    float neg_max = -INFINITY;
+    for (int o0 = 0; o0 < n_q; o0 += 32) {
+      const int o = o0 + lane;
+      neg_max = fmaxf(neg_max, (o < n_q && o != obj) ? srow[o] : -INFINITY);
     }
-  }
-  // approximate arg-max of the negatives (fp32 similarities of the GEMM) and the selection tolerance
-  float neg_max = -INFINITY;
-  for (int o = 0; o < n_q; ++o)
-    if (o != obj) neg_max = fmaxf(neg_max, srow[o]);
-  const float tol = 1e-5f * fmaxf(fmaxf(fabsf(mn), fabsf(mx)), 1e-30f);
-  const float* q0 = queries + query_off[s] * (int64_t)dim;
-  double pos = 0.0, red = (sim_kernel == DC_SIM_MAX) ? -INFINITY : 0.0;
-  bool nan_seen = false;
-  for (int o = 0; o < n_q; ++o) {
-    const float so = srow[o];
-    const bool take = (o == obj) || (sim_kernel == DC_SIM_MEAN) || !(so < neg_max - tol);  // NaN similarities are taken
-    if (!take) continue;  // warp-uniform
-    const float* q = q0 + (int64_t)o * dim;
-    double d = 0.0;
+    neg_max = dc::warp_max(neg_max);
+    double pos = 0.0, red = (sim_kernel == DC_SIM_MAX) ? -INFINITY : 0.0;
+    bool nan_seen = false;
+    for (int o0 = 0; o0 < n_q; o0 += 32) {
+      const int o_mine = o0 + lane;
+      const float so = o_mine < n_q ? srow[o_mine] : -INFINITY;
+      // NaN similarities are taken (the comparison is false for them), so they propagate like in torch
+      const bool take = o_mine < n_q && (o_mine == obj || sim_kernel == DC_SIM_MEAN || !(so < neg_max - tol));
+      unsigned todo = __ballot_sync(0xffffffffu, take);
+      while (todo) {
+        const int o = o0 + __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float* q = q0 + (int64_t)o * dim;
+        double d = 0.0;
+        if (kVec) {
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k)
-      if (k * 32 + lane < dim) d = fma((double)y[k], (double)__ldg(q + k * 32 + lane), d);
+          for (int k = 0; k < 4; ++k)
+            if (k < n_chunks) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(q) + (k * 32 + lane) * 2);
+              const float4 b = __ldg(reinterpret_cast<const float4*>(q) + (k * 32 + lane) * 2 + 1);
+              d = fma((double)y[k * 8 + 0], (double)a.x, d);
+              d = fma((double)y[k * 8 + 1], (double)a.y, d);
+              d = fma((double)y[k * 8 + 2], (double)a.z, d);
+              d = fma((double)y[k * 8 + 3], (double)a.w, d);
+              d = fma((double)y[k * 8 + 4], (double)b.x, d);
+              d = fma((double)y[k * 8 + 5], (double)b.y, d);
+              d = fma((double)y[k * 8 + 6], (double)b.z, d);
+              d = fma((double)y[k * 8 + 7], (double)b.w, d);
+            }
+        } else {
 #pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sh);
-    if (o == obj) pos = d;
-    else {
-      nan_seen |= (d != d);
-      if (sim_kernel == DC_SIM_MAX) red = fmax(red, d);
-      else red += d;
+          for (int k = 0; k < kMaxPerLane; ++k)
+            if (k * 32 + lane < dim) d = fma((double)y[k], (double)__ldg(q + k * 32 + lane), d);
+        }
+        d = warp_sum_f64(d);
+        if (o == obj) pos = d;
+        else {
+          nan_seen |= (d != d);
+          if (sim_kernel == DC_SIM_MAX) red = fmax(red, d);
+          else red += d;
+        }
+      }
     }
+    if (sim_kernel == DC_SIM_MEAN) red = red / (double)(n_q - 1);
+    if (nan_seen) red = __longlong_as_double(0x7ff8000000000000ll);
+    float w = (float)((pos - red) / ((double)mx - (double)mn));  // NaN extrema (a NaN anywhere in the view) give NaN, like torch
+    if (w == w) w = fmaxf(w, 1e-6f);
+    if (lane == 0) *w_slot = w;
   }
-  if (sim_kernel == DC_SIM_MEAN) red = red / (double)(n_q - 1);
-  if (nan_seen) red = __longlong_as_double(0x7ff8000000000000ll);
-  float w = (float)((pos - red) / ((double)mx - (double)mn));  // NaN extrema (a NaN anywhere in the view) give NaN, like torch
-  if (w == w) w = fmaxf(w, 1e-6f);
-  if (lane == 0) weight_obj[wobj_off[s] + (int64_t)obj * n_v + v_local] = w;
 }
 
 __global__ void init_minmax_kernel(float* m) {
@@ -659,35 +725,46 @@ int dc_view_score(const void* feats, int feat_dtype, int64_t total_rows, int dim
   return launch_bn(bn, a_hi, a_lo, total_rows, q_hi, q_lo, total_queries, p, epi, w.max_tiles, st);
 }
 
+size_t dc_view_weights_scratch(int64_t total_views, int64_t total_rows) {
+  return sizeof(float) * 2 * (size_t)(total_views > 0 ? total_views : 0) + sizeof(int) * (1 + 2 * (size_t)(total_rows > 0 ? total_rows : 0));
+}
+
 int dc_view_weights(const float* sims, int sims_ld, const int64_t* feat_off, const int32_t* view_scene,
                     const int64_t* view_off, const int64_t* query_off, const int64_t* wobj_off,
                     const int32_t* row_object, const uint32_t* counts, int nbins, int64_t total_views,
                     int sim_kernel, int use_visibility, float* weight_obj, const void* feats, int feat_dtype, int dim,
-                    const float* queries, int64_t total_rows, float* view_minmax, dc_stream_t stream) {
+                    const float* queries, int64_t total_rows, void* scratch, const void* feats_normalized,
+                    float refine_below, dc_stream_t stream) {
   DC_CHECK_ARG(feat_off && view_scene && view_off && query_off && wobj_off && row_object && weight_obj,
                "dc_view_weights: null pointer argument");
   DC_CHECK_ARG(sim_kernel == DC_SIM_NONE || sims, "dc_view_weights: sims required for a similarity kernel");
   DC_CHECK_ARG(!use_visibility || counts, "dc_view_weights: counts required for use_visibility");
   DC_CHECK_ARG(sim_kernel >= DC_SIM_NONE && sim_kernel <= DC_SIM_MEAN, "dc_view_weights: Please set method in [mean, max]");
   const bool refine = feats && sim_kernel != DC_SIM_NONE;
-  DC_CHECK_ARG(!refine || (queries && view_minmax && dim > 0 && dim <= 1024 && (feat_dtype == DC_F16 || feat_dtype == DC_F32)),
-               "dc_view_weights: exact weights need queries, view_minmax and fp16/fp32 features of dim <= 1024");
+  DC_CHECK_ARG(!refine || (queries && scratch && dim > 0 && dim <= 1024 && (feat_dtype == DC_F16 || feat_dtype == DC_F32)),
+               "dc_view_weights: exact weights need queries, scratch and fp16/fp32 features of dim <= 1024");
+  DC_CHECK_ARG(!refine || ((uintptr_t)scratch & 3) == 0, "dc_view_weights: scratch must be 4-byte aligned");
+  DC_CHECK_ARG(total_rows < (1ll << 31) && total_views < (1ll << 31), "dc_view_weights: too many rows");
   if (total_views <= 0) return DC_OK;
   cudaStream_t st = dc::as_stream(stream);
+  float* view_minmax = refine ? static_cast<float*>(scratch) : nullptr;
+  int* refine_list = refine ? reinterpret_cast<int*>(view_minmax + 2 * total_views) : nullptr;  // [0] count, then (row, view)
+  if (refine) DC_CUDA(cudaMemsetAsync(refine_list, 0, sizeof(int), st));
   view_weights_kernel<<<(unsigned)dc::ceil_div<int64_t>(total_views, 4), 128, 0, st>>>(
       sims, sims_ld, feat_off, view_scene, view_off, query_off, wobj_off, row_object, counts, nbins, total_views,
-      sim_kernel, use_visibility, weight_obj, refine ? view_minmax : nullptr);
+      sim_kernel, use_visibility, weight_obj, view_minmax, refine_list, refine_below);
   DC_LAUNCH_CHECK();
   if (refine && total_rows > 0) {
-    const unsigned grid = (unsigned)dc::ceil_div<int64_t>(total_rows, 8);
-    if (feat_dtype == DC_F16)
-      refine_weights_kernel<__half><<<grid, 256, 0, st>>>((const __half*)feats, dim, queries, sims, sims_ld, feat_off, view_scene,
-                                                         view_off, query_off, wobj_off, row_object, view_minmax, total_views,
-                                                         total_rows, sim_kernel, weight_obj);
-    else
-      refine_weights_kernel<float><<<grid, 256, 0, st>>>((const float*)feats, dim, queries, sims, sims_ld, feat_off, view_scene,
-                                                        view_off, query_off, wobj_off, row_object, view_minmax, total_views,
-                                                        total_rows, sim_kernel, weight_obj);
+    const unsigned grid = (unsigned)std::min<int64_t>(dc::ceil_div<int64_t>(total_rows, 8), (int64_t)dc::sm_count() * 2);
+    const __half* normed = (const __half*)feats_normalized;
+    const bool vec = dim % 256 == 0 && (((uintptr_t)feats | (uintptr_t)feats_normalized | (uintptr_t)queries) & 15) == 0;
+#define DC_REFINE(T, V)                                                                                                     \
+  refine_weights_kernel<T, V><<<grid, 256, 0, st>>>((const T*)feats, normed, dim, queries, sims, sims_ld, feat_off, view_scene, \
+                                                    view_off, query_off, wobj_off, row_object, view_minmax, sim_kernel,       \
+                                                    refine_list, weight_obj)
+    if (feat_dtype == DC_F16) { if (vec) DC_REFINE(__half, true); else DC_REFINE(__half, false); }
+    else { normed = nullptr; if (vec) DC_REFINE(float, true); else DC_REFINE(float, false); }
+#undef DC_REFINE
     DC_LAUNCH_CHECK();
   }
   return DC_OK;

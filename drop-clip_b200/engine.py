@@ -444,6 +444,8 @@ class FusionEngine:
             raise RuntimeError("dropclip_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.device = torch.device(device)
         self.launches = 0  # kernels launched by this engine (bench.py's gpu_launches)
+        # object-level similarity weights below this are re-evaluated in fp64 (dc_view_weights); inf = every row
+        self.refine_below = float(os.environ.get("DC_REFINE_BELOW", "0.02"))
         self.profile: Optional[Dict[str, list]] = None  # name -> [(start_event, end_event)] when enabled
 
     def _tick(self, name: str):
@@ -586,18 +588,21 @@ class FusionEngine:
                                              ptr(b.queries), ptr(b.off["query"]), b.total_queries, b.n_scenes, max_q,
                                              ptr(sims), ld, ptr(ws), ws_bytes, current_stream()))
             self.launches += 4
-        view_mm = torch.empty(max(2 * b.total_views, 2), dtype=torch.float32, device=b.device) if use_similarity else None
+        view_mm = torch.empty(self.lib.dc_view_weights_scratch(b.total_views, b.total_rows) // 4 + 1, dtype=torch.int32,
+                              device=b.device) if use_similarity else None
         check(self.lib.dc_view_weights(ptr(sims), ld, ptr(b.off["feat"]), ptr(b.off["view_scene"]), ptr(b.off["view"]),
                                        ptr(b.off["query"]), ptr(b.off["wobj"]), ptr(row_object), ptr(counts), int(counts.shape[1]),
                                        b.total_views, kern, int(bool(use_visibility)), ptr(weight),
                                        ptr(b.feats) if use_similarity else None, _lib.torch_dtype_code(b.feats.dtype), dim,
-                                       ptr(b.queries) if use_similarity else None, b.total_rows, ptr(view_mm), current_stream()))
+                                       ptr(b.queries) if use_similarity else None, b.total_rows, ptr(view_mm),
+                                       ptr(ws) if (use_similarity and b.feats.dtype == torch.float16) else None,
+                                       float(self.refine_below), current_stream()))
         fused = torch.empty((b.total_queries, dim), dtype=torch.float32, device=b.device)
         with self._tick("segmented_wmean"):
             check(self.lib.dc_segmented_wmean(ptr(b.feats), _lib.torch_dtype_code(b.feats.dtype), dim, ptr(object_row),
                                               ptr(weight), ptr(b.off["view"]), ptr(b.off["query"]), ptr(b.off["wobj"]),
                                               b.n_scenes, max_q, ptr(fused), current_stream()))
-        self.launches += 3 if use_similarity else 2
+        self.launches += 4 if use_similarity else 2  # weights (+ memset node, + refinement), weighted mean
         return fused, weight
 
     def compact_rows(self, t: torch.Tensor, any_vis, new_index, n_kept: int) -> torch.Tensor:

@@ -176,16 +176,21 @@ DC_API int dc_view_score(const void* feats, int feat_dtype, int64_t total_rows, 
  * use_visibility writes the pixel count of the object instead; DC_SIM_NONE without visibility
  * writes 1. Similarity overrides visibility like the reference (quirk q8).
  * weight_obj: wobj layout, fp32, must be zero-filled by the caller.
- * Exact weights (feats != NULL, sim_kernel != NONE): `sims` then only selects - the positive and the negatives within
- * 1e-5 of the arg-max (all of them for DC_SIM_MEAN) are re-evaluated as fp64 dot products of the normalised feature
- * row with the queries and the weight (s_pos - red(s_neg)) / (max - min) is formed in fp64, so weights next to the
- * 1e-6 clip keep a relative accuracy of ~1e-7 instead of the GEMM's absolute 1e-7. feats [total_rows, dim] as given
- * to dc_view_score, queries [total_queries, dim] fp32, view_minmax [2 * total_views] fp32 scratch. */
+ * Exact weights (feats != NULL, sim_kernel != NONE): for rows whose weight from `sims` is below `refine_below` (pass
+ * +inf to re-evaluate every row) `sims` only selects - the positive and the negatives within 1e-5 of the arg-max
+ * (all of them for DC_SIM_MEAN) are re-evaluated as fp64 dot products of the normalised feature row with the queries
+ * and the weight (s_pos - red(s_neg)) / (max - min) is formed in fp64, so weights next to the 1e-6 clip keep a
+ * relative accuracy of ~1e-7 instead of the GEMM's absolute 1e-7. feats [total_rows, dim] as given to dc_view_score,
+ * queries [total_queries, dim] fp32, scratch: dc_view_weights_scratch(total_views, total_rows) bytes (4-byte aligned;
+ * per-view extrema and the queue of rows to re-evaluate), feats_normalized: for fp16 features the fp16 plane of
+ * normalised rows dc_view_score left at the start of its workspace (or NULL: normalised here). */
+DC_API size_t dc_view_weights_scratch(int64_t total_views, int64_t total_rows);
 DC_API int dc_view_weights(const float* sims, int sims_ld, const int64_t* feat_off, const int32_t* view_scene,
                     const int64_t* view_off, const int64_t* query_off, const int64_t* wobj_off,
                     const int32_t* row_object, const uint32_t* counts, int nbins, int64_t total_views,
                     int sim_kernel, int use_visibility, float* weight_obj, const void* feats, int feat_dtype, int dim,
-                    const float* queries, int64_t total_rows, float* view_minmax, dc_stream_t stream);
+                    const float* queries, int64_t total_rows, void* scratch, const void* feats_normalized,
+                    float refine_below, dc_stream_t stream);
 
 /* (4) Object-level segmented weighted mean over views. Replaces the einsum and division at
  * utils/feature_fusion.py:333-335:  fused[query_off[s]+o, :] = sum_v w[o,v] * feat[row(o,v)] / sum_v w[o,v]

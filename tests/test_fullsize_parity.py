@@ -206,3 +206,39 @@ def test_full_scene_pixel_fusion_vs_reference_golden(pix_case):
     got, ref, exact, nrm = f64.sum(1), z["feat_row_sum"].astype(np.float64), z["feat_row_sum_exact"], z["feat_row_norm_exact"]
     assert (np.abs(got - exact) <= 1e-3 * nrm).all()
     assert (np.abs(got - ref) <= 1e-3 * nrm + np.abs(ref - exact)).all()
+
+
+# ---------------------------------------------------------------------------------------------- ill-conditioned weights
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("sim", ["max", "mean"])
+def test_object_weights_next_to_the_clip_are_exact(dtype, sim):
+    """Two queries that nearly coincide make pos - max(neg) land between the 1e-6 clip and ~1e-4: the tensor-core GEMM
+    (and the reference's own sgemm) resolve such a difference to ~1e-7 absolute only. dc_view_weights re-evaluates
+    weights below `refine_below` in fp64; they must match the float64 evaluation of the reference's formulas to 1e-3
+    (exact_close, every element), with and without forcing the re-evaluation of every row."""
+    from dropclip_b200.engine import intrinsic_matrix
+    from dropclip_b200.scenes import small_scene
+    from oracle import fusion_ref
+    sc = small_scene(31337, n_views=6, n_points=3000, n_objects=8, height=120, width=160, feature_dtype=dtype)
+    rng = np.random.default_rng(2)
+    q = sc.query_embeddings.clone()
+    for a, b, eps in ((1, 2, 3e-5), (3, 4, 2e-6), (5, 6, 4e-4)):   # object b's query is object a's, nudged
+        nudged = q[a] + eps * torch.from_numpy(rng.standard_normal(768).astype(np.float32))
+        q[b] = nudged / nudged.norm()
+    sc.query_embeddings = q
+    K = intrinsic_matrix(sc.intrinsic)
+    args = (sc.points, sc.colors, sc.labels, sc.depths, sc.seg_masks, sc.camera_poses, sc.mv_features, sc.query_embeddings, K,
+            120, 160)
+    (rf, rw, _), _ = fusion_ref.fuse_object_level(*args, sim_method=sim, return_obj=True)
+    (xf, xw, _), _ = fusion_ref.fuse_object_level(*args, sim_method=sim, return_obj=True, work=torch.float64)
+    small = (xw.numpy() > 0) & (xw.numpy() < 0.02)
+    assert small.sum() >= 6, "the case must produce weights next to the clip"
+    for refine_below in (0.02, float("inf")):
+        M = mvff(sc, use_visibility=0, use_similarity=1, use_sim_kernel=sim, use_obj_prior=1, norm_feat=False)
+        M._eng("cuda").refine_below = refine_below
+        (f, w, _), _ = M.fuse(sc.points, sc.colors, sc.labels, sc.depths, sc.seg_masks, sc.camera_poses, sc.mv_features,
+                              sc.query_embeddings, return_obj=True, device="cuda")
+        exact_close(w.cpu().numpy(), rw.numpy(), xw.numpy(), what=f"weights next to the clip ({sim}, refine_below={refine_below})")
+        exact_close(f.cpu().numpy(), rf.numpy(), xf.numpy(), what=f"features under such weights ({sim}, refine_below={refine_below})")
+        got, want = w.cpu().numpy()[small], xw.numpy()[small]
+        assert (np.abs(got - want) <= 1e-3 * np.abs(want) + 1e-12).all(), "re-evaluated weights must be exact to 1e-3 RELATIVE"
