@@ -766,7 +766,15 @@ struct ConstBankTurn {
     if (!ev) status = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     else status = cudaStreamWaitEvent(stream, ev, 0);
   }
-  cudaError_t release() { return cudaEventRecord(events()[device], stream); }
+  // Records the "last use" event. Also runs from the destructor, so an error return between the constructor and the
+  // explicit release() still orders the next user of the bank behind the kernels this call did enqueue.
+  cudaError_t release() {
+    if (released || status != cudaSuccess) return cudaSuccess;
+    released = true;
+    return cudaEventRecord(events()[device], stream);
+  }
+  ~ConstBankTurn() { (void)release(); }
+  bool released = false;
 };
 
 // scenes per filter launch: bounded by the constant bank and by one full wave of CTAs; balanced
