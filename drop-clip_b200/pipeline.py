@@ -33,8 +33,8 @@ from .engine import FusionEngine, PinnedStaging, SceneBatch, _labels_as_int64, i
 __all__ = ["PinnedSceneSlot", "SceneResult", "FusionPipeline"]
 
 
-def _pinned(shape, dtype) -> torch.Tensor:
-    return torch.empty(shape, dtype=dtype, pin_memory=True)
+def _pinned(shape, dtype, pin: bool = True) -> torch.Tensor:
+    return torch.empty(shape, dtype=dtype, pin_memory=pin)
 
 
 class PinnedSceneSlot:
@@ -42,17 +42,20 @@ class PinnedSceneSlot:
     or `fill(...)` from the reference's containers) and hands the slot to `FusionPipeline.submit`."""
 
     def __init__(self, height: int, width: int, max_views: int, max_points: int, max_rows: int, max_queries: int,
-                 feat_dim: int = 768, feat_dtype=torch.float16):
+                 feat_dim: int = 768, feat_dtype=torch.float16, pinned: bool = True):
+        """`pinned=False` gives ordinary host memory (host-logic tests of loaders without a GPU; the pipeline itself
+        always allocates pinned slots)."""
         self.height, self.width = height, width
         self.cap = dict(views=max_views, points=max_points, rows=max_rows, queries=max_queries)
-        self.t_depths = _pinned((max_views, height, width), torch.float32)
-        self.t_segs = _pinned((max_views, height, width), torch.uint8)
+        self._pin = pinned
+        self.t_depths = _pinned((max_views, height, width), torch.float32, pinned)
+        self.t_segs = _pinned((max_views, height, width), torch.uint8, pinned)
         self.t_segs_wide: Optional[torch.Tensor] = None  # int64 maps, allocated on first use (an id outside [0, 255])
-        self.t_inv_poses = _pinned((max_views, 16), torch.float64)
-        self.t_points = _pinned((max_points, 3), torch.float64)
-        self.t_labels = _pinned((max_points,), torch.int64)
-        self.t_feats = _pinned((max_rows, feat_dim), feat_dtype)
-        self.t_queries = _pinned((max_queries, feat_dim), torch.float32)
+        self.t_inv_poses = _pinned((max_views, 16), torch.float64, pinned)
+        self.t_points = _pinned((max_points, 3), torch.float64, pinned)
+        self.t_labels = _pinned((max_points,), torch.int64, pinned)
+        self.t_feats = _pinned((max_rows, feat_dim), feat_dtype, pinned)
+        self.t_queries = _pinned((max_queries, feat_dim), torch.float32, pinned)
         # numpy views for loaders
         self.depths, self.segs = self.t_depths.numpy(), self.t_segs.numpy()
         self.inv_poses, self.points, self.labels = self.t_inv_poses.numpy(), self.t_points.numpy(), self.t_labels.numpy()
@@ -87,33 +90,53 @@ class PinnedSceneSlot:
         dl = [np.ascontiguousarray(d, dtype=np.float32) for d in depths]
         srcs = (ctypes.c_void_p * V)(*[d.ctypes.data for d in dl])
         _lib.check(lib.dc_host_gather_copy(srcs, V, hw * 4, ctypes.c_void_p(self.t_depths.data_ptr()), threads))
-        sl = [np.ascontiguousarray(s.cpu().numpy() if isinstance(s, torch.Tensor) else s) for s in seg_masks]
-        self.wide_segs = False
-        if all(s.dtype == np.uint8 for s in sl):
-            for v, s in enumerate(sl):
-                self.segs[v] = s
-        else:
-            sl = [s.astype(np.int64, copy=False) for s in sl]
-            srcs = (ctypes.c_void_p * V)(*[s.ctypes.data for s in sl])
-            bad = ctypes.c_int(0)
-            _lib.check(lib.dc_host_gather_narrow_i64_u8(srcs, V, hw, ctypes.c_void_p(self.t_segs.data_ptr()), threads,
-                                                        ctypes.byref(bad)))
-            if bad.value:  # an id outside [0, 255] (e.g. a -1 background): ship the int64 maps unchanged
-                if self.t_segs_wide is None:
-                    self.t_segs_wide = _pinned((self.cap["views"], self.height, self.width), torch.int64)
-                _lib.check(lib.dc_host_gather_copy(srcs, V, hw * 8, ctypes.c_void_p(self.t_segs_wide.data_ptr()), threads))
-                self.wide_segs = True
+        self.store_segs(seg_masks, threads)
         self.set_poses(camera_poses)
-        self.points[:N] = np.asarray(points, dtype=np.float64).reshape(N, 3)
-        self.labels[:N] = _labels_as_int64(labels)
         r0 = 0
         for v, f in enumerate(mv_features):
             if f.shape[-1] != self.t_feats.shape[1]:
                 raise RuntimeError(f"The expanded size of the tensor ({self.t_feats.shape[1]}) must match the existing size ({f.shape[-1]})")
             self.t_feats[r0:r0 + rows[v]].copy_(f)
-            self.feat_rows[v] = rows[v]
             r0 += rows[v]
         self.t_queries[:Q].copy_(query_embeddings)
+        return self.set_scene(V, N, Q, rows, points, colors, labels)
+
+    def store_segs(self, seg_masks, threads: int = 0) -> None:
+        """Instance maps (a list of (H,W) arrays or one (V,H,W) array, any integer dtype) into the slot: as uint8 when
+        every id fits a byte, else unchanged as int64 (`wide_segs`; e.g. a -1 background, which np.unique()[1:] drops)."""
+        lib = _lib.load()
+        threads = threads or PinnedStaging._host_threads()
+        hw = self.height * self.width
+        sl = [np.ascontiguousarray(s.cpu().numpy() if isinstance(s, torch.Tensor) else s) for s in seg_masks]
+        V = len(sl)
+        if V > self.cap["views"]:
+            raise ValueError(f"{V} views exceed the slot capacity {self.cap['views']}")
+        self.wide_segs = False
+        if all(s.dtype == np.uint8 for s in sl):
+            for v, s in enumerate(sl):
+                self.segs[v] = s
+            return
+        sl = [s.astype(np.int64, copy=False) for s in sl]
+        srcs = (ctypes.c_void_p * V)(*[s.ctypes.data for s in sl])
+        bad = ctypes.c_int(0)
+        _lib.check(lib.dc_host_gather_narrow_i64_u8(srcs, V, hw, ctypes.c_void_p(self.t_segs.data_ptr()), threads,
+                                                    ctypes.byref(bad)))
+        if bad.value:  # an id outside [0, 255]: ship the int64 maps unchanged
+            if self.t_segs_wide is None:
+                self.t_segs_wide = _pinned((self.cap["views"], self.height, self.width), torch.int64, self._pin)
+            _lib.check(lib.dc_host_gather_copy(srcs, V, hw * 8, ctypes.c_void_p(self.t_segs_wide.data_ptr()), threads))
+            self.wide_segs = True
+
+    def set_scene(self, n_views: int, n_points: int, n_queries: int, feat_rows, points, colors, labels):
+        """Extents + the per-point arrays, for loaders that wrote depths / segs / feats / queries / poses in place.
+        `points`, `colors`, `labels` are kept by reference for the lazily filtered outputs (they must not alias the slot)."""
+        rows = [int(r) for r in feat_rows]
+        V, N, Q = int(n_views), int(n_points), int(n_queries)
+        if V > self.cap["views"] or N > self.cap["points"] or Q > self.cap["queries"] or sum(rows) > self.cap["rows"] or len(rows) != V:
+            raise ValueError(f"scene (V={V}, N={N}, Q={Q}, rows={sum(rows)}) exceeds the slot capacity {self.cap}")
+        self.points[:N] = np.asarray(points, dtype=np.float64).reshape(N, 3)
+        self.labels[:N] = _labels_as_int64(labels)
+        self.feat_rows[:V] = rows
         self.n_views, self.n_points, self.n_queries = V, N, Q
         self.points_src, self.colors, self.labels_src = points, colors, labels
         return self
@@ -222,7 +245,9 @@ class FusionPipeline:
             self._free.put(s)
         self._submitted: "queue.Queue[Optional[PinnedSceneSlot]]" = queue.Queue()
         self._inflight: "queue.Queue[Optional[tuple]]" = queue.Queue()
-        self._results: "queue.Queue[Optional[SceneResult]]" = queue.Queue()
+        # bounded: a slow consumer (e.g. the file writers of shard.run_scene_driver) holds back the completion thread,
+        # hence the arenas, hence the slots - instead of results piling up in host memory
+        self._results: "queue.Queue[Optional[SceneResult]]" = queue.Queue(maxsize=8 * self.B + 32)
         self.h2d_bytes = self.d2h_bytes = 0
         self.launches = 0
         self._error: Optional[BaseException] = None
@@ -238,6 +263,10 @@ class FusionPipeline:
             except queue.Empty:
                 if self._error is not None:  # a stage died: do not wait for slots that will never come back
                     raise RuntimeError("FusionPipeline stopped") from self._error
+
+    def release(self, slot: PinnedSceneSlot) -> None:
+        """Hands an acquired slot back unused (the loader gave up on its scene)."""
+        self._free.put(slot)
 
     def submit(self, slot: PinnedSceneSlot, tag: Any = None) -> None:
         slot.tag = tag
