@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libdropclip.so")
 
 DC_F16, DC_F32, DC_U8, DC_I32, DC_I64, DC_F64 = 0, 1, 2, 3, 4, 5
 DC_SIM_NONE, DC_SIM_MAX, DC_SIM_MEAN = 0, 1, 2
-DC_GROUND_RAW, DC_GROUND_PAIRED, DC_GROUND_ARGMAX = 0, 1, 2
+DC_GROUND_RAW, DC_GROUND_PAIRED, DC_GROUND_ARGMAX, DC_GROUND_CLASS = 0, 1, 2, 3
 ABI_VERSION = 2
 
 P = c_void_p
@@ -58,7 +58,8 @@ SIGNATURES = {
     "dc_voxel_gather": (c_int, [P, c_int64, P, P, P, c_int, c_int64, P, P]),
     "dc_row_normalize": (c_int, [P, c_int, c_int64, c_int, c_int, P, P, P]),
     "dc_ground_init_minmax": (c_int, [P, P]),
-    "dc_ground": (c_int, [P, P, c_int64, P, P, c_int, c_int, c_int, c_float, P, c_int, P, P, P]),
+    "dc_ground_workspace": (c_size_t, [c_int64, c_int, c_int]),
+    "dc_ground": (c_int, [P, P, c_int64, P, P, c_int, c_int, c_int, c_float, P, c_int, P, P, P, P, c_size_t, P]),
     "dc_minmax_threshold": (c_int, [P, c_int64, P, c_int, c_float, c_int, P, P]),
     "dc_backproject": (c_int, [P, c_int, c_int, c_int, P, c_int, c_int, P, P, P]),
     "dc_points_to_pixels": (c_int, [P, c_int64, P, P, P]),

@@ -259,23 +259,33 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 struct EpiGround {
   int mode;
-  int n_prompts;
+  int n_prompts;   // columns of THIS launch (<= 256)
   float inv_temp;
   float* out;
   int out_ld;
   uint8_t* pred;
   float* minmax;  // [0] min(out) [1] max(out) [2] min(raw) [3] max(raw)
+  // prompt axis cut into blocks of <= 256 columns (one launch each): this launch covers the global columns
+  // [col_base, col_base + n_prompts) of n_total; `carry` [n_points, 4] hands (pos, partial sum, running max, arg max)
+  // from block to block, the last block finishes the row. One block: col_base = 0, last = 1, carry unused.
+  int col_base, n_total, last;
+  float* carry;
+  int64_t* argmax_idx;  // DC_GROUND_CLASS: index of the row maximum (torch.max(sims, 1)[1], engine/distil.py:290)
   // per-thread running state
   float pos, scale, bias, acc[4], neg_max, raw_min, raw_max;
+  int best_idx;
 
-  __device__ __forceinline__ void begin(const Tile&, int, float col0) {
+  __device__ __forceinline__ void begin(const Tile& t, int r, float col0) {
     pos = col0;
+    if (col_base > 0 && mode != DC_GROUND_RAW && mode != DC_GROUND_CLASS)
+      pos = (r < t.rows) ? carry[((int64_t)t.a_row + r) * 4] : 0.f;
     scale = inv_temp * 1.4426950408889634f;  // log2(e) / T
     bias = -pos * scale;
     acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
     neg_max = -INFINITY;
     raw_min = INFINITY;
     raw_max = -INFINITY;
+    best_idx = 0x7fffffff;
   }
 
   template <bool kMasked>
@@ -283,7 +293,7 @@ struct EpiGround {
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const bool valid = !kMasked || (c0 + i < n_prompts);
-      const bool neg = !kMasked || (valid && c0 + i > 0);
+      const bool neg = !kMasked || (valid && col_base + c0 + i > 0);
       if (valid) {
         raw_min = fminf(raw_min, v[i]);
         raw_max = fmaxf(raw_max, v[i]);
@@ -297,56 +307,95 @@ struct EpiGround {
 
   __device__ __forceinline__ void row(const Tile& t, int r, int c0, const float (&v)[32]) {
     if (r >= t.rows) return;
-    if (mode == DC_GROUND_RAW) {
-      float* dst = out + (int64_t)(t.a_row + r) * out_ld + c0;
+    if (mode == DC_GROUND_RAW || mode == DC_GROUND_CLASS) {
       const int n = min(32, n_prompts - c0);
-      if (n == 32 && (out_ld & 3) == 0) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          raw_min = fminf(raw_min, v[i]);
-          raw_max = fmaxf(raw_max, v[i]);
-        }
-      } else {
+      if (mode == DC_GROUND_CLASS) {
+        // first index of the maximum; a NaN is the maximum (torch.max propagates NaN)
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (i < n) {
-            dst[i] = v[i];
-            raw_min = fminf(raw_min, v[i]);
-            raw_max = fmaxf(raw_max, v[i]);
+            const bool take = (v[i] > neg_max) || (v[i] != v[i] && neg_max == neg_max) || best_idx == 0x7fffffff;
+            if (take) { neg_max = v[i]; best_idx = col_base + c0 + i; }
           }
       }
+      if (out) {
+        float* dst = out + (int64_t)(t.a_row + r) * out_ld + c0;
+        if (n == 32 && (out_ld & 3) == 0 && ((uintptr_t)out & 15) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < n) dst[i] = v[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < n) {
+          raw_min = fminf(raw_min, v[i]);
+          raw_max = fmaxf(raw_max, v[i]);
+        }
       return;
     }
-    if (c0 > 0 && c0 + 32 <= n_prompts) chunk<false>(c0, v);  // interior chunk: no masks
-    else chunk<true>(c0, v);                                  // holds the positive column or the ragged end
+    if ((c0 > 0 || col_base > 0) && c0 + 32 <= n_prompts) chunk<false>(c0, v);  // interior chunk: no masks
+    else chunk<true>(c0, v);                                                     // holds the positive column or the ragged end
   }
 
   __device__ __forceinline__ void finish(const Tile& t, int r, int half, int n_halves, float* scratch) {
     float sum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     if (n_halves == 2) {
       // half 1 hands its partials to half 0 through shared memory; barrier 1 is private to the 8 epilogue warps
-      float* slot = scratch + r * 4;
+      float* slot = scratch + r * 8;
       asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done with the scratch
       if (half == 1) {
         slot[0] = sum;
         slot[1] = neg_max;
         slot[2] = raw_min;
         slot[3] = raw_max;
+        slot[4] = __int_as_float(best_idx);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (half == 1) return;
       sum += slot[0];
-      neg_max = fmaxf(neg_max, slot[1]);
+      if (mode == DC_GROUND_CLASS) {  // half 1 holds the higher indices: it wins only with a strictly larger value (or a NaN)
+        const float o_max = slot[1];
+        const int o_idx = __float_as_int(slot[4]);
+        if (o_idx != 0x7fffffff && (best_idx == 0x7fffffff || o_max > neg_max || (o_max != o_max && neg_max == neg_max))) {
+          neg_max = o_max;
+          best_idx = o_idx;
+        }
+      } else {
+        neg_max = fmaxf(neg_max, slot[1]);
+      }
       raw_min = fminf(raw_min, slot[2]);
       raw_max = fmaxf(raw_max, slot[3]);
     }
     const bool have = r < t.rows;
+    const int64_t gr = (int64_t)t.a_row + r;
+    if (have && carry && mode != DC_GROUND_RAW) {
+      float* cr = carry + gr * 4;
+      if (col_base > 0) {
+        if (mode == DC_GROUND_CLASS) {  // earlier blocks hold the lower indices
+          const float p_max = cr[2];
+          const int p_idx = __float_as_int(cr[3]);
+          if (!(neg_max > p_max || (neg_max != neg_max && p_max == p_max))) { neg_max = p_max; best_idx = p_idx; }
+        } else {
+          sum += cr[1];
+          neg_max = fmaxf(neg_max, cr[2]);
+        }
+      }
+      if (!last) {
+        cr[0] = pos;
+        cr[1] = sum;
+        cr[2] = neg_max;
+        cr[3] = __int_as_float(best_idx);
+      }
+    }
     float o = 0.f;
-    if (have && mode != DC_GROUND_RAW) {
-      const int64_t gr = (int64_t)t.a_row + r;
-      const float n_neg = (float)(n_prompts - 1);
+    const bool final_row = have && last;
+    if (final_row && mode == DC_GROUND_CLASS) argmax_idx[gr] = best_idx;
+    if (final_row && (mode == DC_GROUND_PAIRED || mode == DC_GROUND_ARGMAX)) {
+      const float n_neg = (float)(n_total - 1);
       if (mode == DC_GROUND_PAIRED) {
         o = 1.f / (n_neg + sum);
         if (o != o) o = 0.f;  // nan_to_num
@@ -356,10 +405,11 @@ struct EpiGround {
       }
       out[gr] = o;
     }
+    const bool raw_like = (mode == DC_GROUND_RAW || mode == DC_GROUND_CLASS);
     float a = INFINITY, b = -INFINITY, c = INFINITY, d = -INFINITY;
     if (have) {
-      a = (mode == DC_GROUND_RAW) ? raw_min : o;
-      b = (mode == DC_GROUND_RAW) ? raw_max : o;
+      if (raw_like) { a = raw_min; b = raw_max; }
+      else if (last) { a = o; b = o; }
       c = raw_min;
       d = raw_max;
     }
@@ -787,31 +837,57 @@ int dc_ground_init_minmax(float* minmax, dc_stream_t stream) {
   return DC_OK;
 }
 
+size_t dc_ground_workspace(int64_t n_points, int n_prompts, int mode) {
+  if (n_prompts <= 256 || mode == DC_GROUND_RAW || n_points <= 0) return 0;
+  return (size_t)n_points * 4 * sizeof(float);
+}
+
 int dc_ground(const void* x_hi, const void* x_lo, int64_t n_points, const void* t_hi, const void* t_lo, int n_prompts,
-              int dim, int mode, float softmax_temp, float* out, int out_ld, uint8_t* pred, float* minmax,
-              dc_stream_t stream) {
-  DC_CHECK_ARG(x_hi && t_hi && out && minmax, "dc_ground: null pointer argument");
-  DC_CHECK_ARG(n_prompts >= 1 && n_prompts <= 256, "dc_ground: 1..256 prompts per call (got %d)", n_prompts);
+              int dim, int mode, float softmax_temp, float* out, int out_ld, uint8_t* pred, int64_t* argmax_idx,
+              float* minmax, void* workspace, size_t workspace_bytes, dc_stream_t stream) {
+  DC_CHECK_ARG(x_hi && t_hi && minmax, "dc_ground: null pointer argument");
+  DC_CHECK_ARG(out || mode == DC_GROUND_CLASS, "dc_ground: null output");
+  DC_CHECK_ARG(n_prompts >= 1, "dc_ground: at least one prompt (got %d)", n_prompts);
   DC_CHECK_ARG(dim > 0 && dim % 64 == 0, "dc_ground: feature dim must be a multiple of 64 (got %d)", dim);
-  DC_CHECK_ARG(mode >= DC_GROUND_RAW && mode <= DC_GROUND_ARGMAX, "dc_ground: bad mode");
+  DC_CHECK_ARG(mode >= DC_GROUND_RAW && mode <= DC_GROUND_CLASS, "dc_ground: bad mode");
   DC_CHECK_ARG(mode != DC_GROUND_ARGMAX || pred, "dc_ground: argmax mode needs pred");
-  DC_CHECK_ARG(mode == DC_GROUND_RAW || n_prompts >= 2, "dc_ground: paired/argmax need at least one negative prompt");
-  DC_CHECK_ARG(mode != DC_GROUND_RAW || out_ld >= n_prompts, "dc_ground: out_ld < n_prompts");
+  DC_CHECK_ARG(mode != DC_GROUND_CLASS || argmax_idx, "dc_ground: class mode needs argmax_idx");
+  DC_CHECK_ARG(mode == DC_GROUND_RAW || mode == DC_GROUND_CLASS || n_prompts >= 2,
+               "dc_ground: paired/argmax need at least one negative prompt");
+  DC_CHECK_ARG((mode != DC_GROUND_RAW && mode != DC_GROUND_CLASS) || !out || out_ld >= n_prompts, "dc_ground: out_ld < n_prompts");
   DC_CHECK_ARG(n_points < (1ll << 31), "dc_ground: too many points for one call");
   if (n_points <= 0) return DC_OK;
-  const int bn = pick_bn(n_prompts);
+  const size_t need = dc_ground_workspace(n_points, n_prompts, mode);
+  if (need > 0 && (!workspace || workspace_bytes < need))
+    return dc::fail(DC_ERR_WORKSPACE, "dc_ground: %zu workspace bytes needed for %d prompts, got %zu", need, n_prompts, workspace_bytes);
   const int n_terms = x_lo ? 3 : (t_lo ? 2 : 1);
-  Params p{nullptr, nullptr, n_points, n_prompts, dim, n_terms};
-  EpiGround epi{};
-  epi.mode = mode;
-  epi.n_prompts = n_prompts;
-  epi.inv_temp = 1.0f / softmax_temp;
-  epi.out = out;
-  epi.out_ld = out_ld;
-  epi.pred = pred;
-  epi.minmax = minmax;
   const int max_tiles = (int)dc::ceil_div<int64_t>(n_points, dc::gemm::kBlockM);
-  return launch_bn(bn, x_hi, x_lo, n_points, t_hi, t_lo ? t_lo : t_hi, n_prompts, p, epi, max_tiles, dc::as_stream(stream));
+  // the prompt axis in blocks of <= 256 columns (the widest UMMA N): partial sums / maxima of the paired softmax,
+  // the mean of the negatives and the arg max combine across blocks through `carry` (models/similarity.py:47-61
+  // has no prompt limit; tools/preprocess_data.py use_kernel_neg == 'all' concatenates the whole class table)
+  for (int c0 = 0; c0 < n_prompts; c0 += 256) {
+    const int cols = n_prompts - c0 < 256 ? n_prompts - c0 : 256;
+    const int bn = pick_bn(cols);
+    Params p{nullptr, nullptr, n_points, cols, dim, n_terms};
+    EpiGround epi{};
+    epi.mode = mode;
+    epi.n_prompts = cols;
+    epi.inv_temp = 1.0f / softmax_temp;
+    epi.out = (mode == DC_GROUND_RAW || mode == DC_GROUND_CLASS) ? (out ? out + c0 : nullptr) : out;
+    epi.out_ld = out_ld;
+    epi.pred = pred;
+    epi.minmax = minmax;
+    epi.col_base = c0;
+    epi.n_total = n_prompts;
+    epi.last = (c0 + cols >= n_prompts) ? 1 : 0;
+    epi.carry = need ? (float*)workspace : nullptr;
+    epi.argmax_idx = argmax_idx;
+    const char* th = (const char*)t_hi + (size_t)c0 * dim * 2;
+    const char* tl = t_lo ? (const char*)t_lo + (size_t)c0 * dim * 2 : th;
+    const int rc = launch_bn(bn, x_hi, x_lo, n_points, th, tl, cols, p, epi, max_tiles, dc::as_stream(stream));
+    if (rc) return rc;
+  }
+  return DC_OK;
 }
 
 int dc_minmax_threshold(float* values, int64_t n, const float* minmax, int use_raw_extrema_for_test, float threshold,

@@ -730,9 +730,11 @@ class FusionEngine:
 
     # ------------------------------------------------------------------ (6) grounding
     def ground(self, feats: torch.Tensor, text: torch.Tensor, mode: int, softmax_temp: float = 0.1,
-               normalize: bool = True):
+               normalize: bool = True, want_matrix: bool = True):
         """feats (N,C) fp16/fp32 CUDA tensor (normalised IN PLACE when `normalize`), text (P,C) already
-        normalised prompt embeddings, prompt 0 positive. Returns (out, pred|None, minmax[4])."""
+        normalised prompt embeddings (any P: the kernel walks the prompt axis in blocks of 256), prompt 0 positive.
+        Returns (out, pred|None, minmax[4]); DC_GROUND_CLASS: out = (N,P) raw similarities (None unless
+        `want_matrix`) and pred = (N,) int64 index of each row's maximum."""
         n, dim = feats.shape
         p = int(text.shape[0])
         dev = feats.device
@@ -752,19 +754,23 @@ class FusionEngine:
         check(self.lib.dc_row_normalize(ptr(t32), _lib.DC_F32, p, dim, 0, ptr(tplanes[0]), ptr(tplanes[1]), current_stream()))
         minmax = torch.empty(4, dtype=torch.float32, device=dev)
         check(self.lib.dc_ground_init_minmax(ptr(minmax), current_stream()))
-        pred = None
-        if mode == _lib.DC_GROUND_RAW:
-            out = torch.empty((n, p), dtype=torch.float32, device=dev)
+        pred = argmax_idx = None
+        if mode in (_lib.DC_GROUND_RAW, _lib.DC_GROUND_CLASS):
+            out = torch.empty((n, p), dtype=torch.float32, device=dev) if (want_matrix or mode == _lib.DC_GROUND_RAW) else None
             ld = p
+            if mode == _lib.DC_GROUND_CLASS:
+                argmax_idx = torch.empty(n, dtype=torch.int64, device=dev)
         else:
             out = torch.empty(n, dtype=torch.float32, device=dev)
             ld = 1
             if mode == _lib.DC_GROUND_ARGMAX:
                 pred = torch.empty(n, dtype=torch.uint8, device=dev)
+        ws_bytes = self.lib.dc_ground_workspace(n, p, mode)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
         check(self.lib.dc_ground(ptr(x_hi), ptr(x_lo), n, ptr(tplanes[0]), ptr(t_lo), p, dim, mode, float(softmax_temp),
-                                 ptr(out), ld, ptr(pred), ptr(minmax), current_stream()))
-        self.launches += 4
-        return out, pred, minmax
+                                 ptr(out), ld, ptr(pred), ptr(argmax_idx), ptr(minmax), ptr(ws), ws_bytes, current_stream()))
+        self.launches += 3 + (p + 255) // 256
+        return out, (argmax_idx if mode == _lib.DC_GROUND_CLASS else pred), minmax
 
     def minmax_threshold(self, values, minmax, use_raw: bool, threshold: float, want_pred: bool):
         pred = torch.empty(values.numel(), dtype=torch.uint8, device=values.device) if want_pred else None

@@ -115,18 +115,30 @@ def apply_pca(features, norm=True, seed=42):
     return X
 
 
+def _center_crop(arr: np.ndarray, size: int) -> np.ndarray:
+    """torchvision.transforms.CenterCrop([size, size]) on an (H, W[, C]) array, as utils/projections.py:119-125 applies it
+    to the depth image (through PIL) and to the feature map: zero padding when the image is smaller than the crop
+    (left/top get the floor half, right/bottom the ceil half), then the window at round((dim - size) / 2)."""
+    h, w = arr.shape[:2]
+    if size > w or size > h:
+        pl, pt = ((size - w) // 2 if size > w else 0), ((size - h) // 2 if size > h else 0)
+        pr, pb = ((size - w + 1) // 2 if size > w else 0), ((size - h + 1) // 2 if size > h else 0)
+        arr = np.pad(arr, [(pt, pb), (pl, pr)] + [(0, 0)] * (arr.ndim - 2))
+        h, w = arr.shape[:2]
+        if (h, w) == (size, size):
+            return np.ascontiguousarray(arr)
+    top, left = int(round((h - size) / 2.0)), int(round((w - size) / 2.0))
+    return np.ascontiguousarray(arr[top:top + size, left:left + size])
+
+
 def project_2d_features_to_3d(depth_image, features, camera_intrinsics, center_crop=None, transform_to_world=False,
                               transform_coords=_cvt_regrad_coord, subsample_step=1, camera_extrinsics=None):
     """utils/projections.py:108-147: optional centre crop, back-projection, axis flip, strided
     sub-sampling, camera->world."""
     if center_crop:
-        h, w = depth_image.shape[:2]
-        top, left = int(round((h - center_crop) / 2.0)), int(round((w - center_crop) / 2.0))  # torchvision CenterCrop
-        depth_image = np.ascontiguousarray(depth_image[top:top + center_crop, left:left + center_crop])
-        if depth_image.shape[0:2] != features.shape[0:2]:
-            fh, fw = features.shape[:2]
-            ft, fl = int(round((fh - center_crop) / 2.0)), int(round((fw - center_crop) / 2.0))
-            features = features[ft:ft + center_crop, fl:fl + center_crop]
+        depth_image = _center_crop(np.asarray(depth_image), int(center_crop))
+        if depth_image.shape[0:2] != features.shape[0:2]:  # crop features if not already aligned (:123-125)
+            features = _center_crop(np.asarray(features), int(center_crop))
     pc = backproject(depth_image, camera_intrinsics)[0].reshape(-1, 3).cpu().numpy()
     features = features.reshape(-1, features.shape[-1])
     if transform_coords is not None:

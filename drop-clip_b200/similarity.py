@@ -18,7 +18,6 @@ from .engine import FusionEngine
 
 DEVICE = torch.device("cuda")  # the reference's expression always evaluates to 'cuda' (quirk q20)
 
-MAX_PROMPTS = 256
 
 
 def _load_clip(model_name, device):
@@ -92,8 +91,6 @@ class ClipSimilarity(object):
         eng = self._eng()
         text = qp if qn is None else torch.cat([qp, qn], dim=0)
         text = text.to(vis_feat_norm.device)
-        if text.shape[0] > MAX_PROMPTS:
-            raise RuntimeError(f"at most {MAX_PROMPTS} prompts per call")
         if qn is not None and method == "paired":
             out, _, _ = eng.ground(vis_feat_norm, text, _lib.DC_GROUND_PAIRED, softmax_temp, normalize=False)
             return out.view(-1, 1).to(vis_feat_norm.dtype)
@@ -112,8 +109,6 @@ class ClipSimilarity(object):
         qp, qn = self._encode(qpos, qneg)
         eng = self._eng()
         text = (qp if qn is None else torch.cat([qp, qn], dim=0)).to(vis_feats.device)
-        if text.shape[0] > MAX_PROMPTS:
-            raise RuntimeError(f"at most {MAX_PROMPTS} prompts per call")
         n = vis_feats.shape[0]
         if qneg is None or (qneg is not None and method == "paired"):
             mode = _lib.DC_GROUND_RAW if qn is None else _lib.DC_GROUND_PAIRED
@@ -130,3 +125,38 @@ class ClipSimilarity(object):
             out, pred, mm = eng.ground(vis_feats, text, _lib.DC_GROUND_ARGMAX, self.SOFTMAX_TEMP, normalize=bool(norm_vis_feat))
             eng.minmax_threshold(out, mm, True, threshold, False)
             return pred.bool(), out
+
+
+# ---------------------------------------------------------------------- a18
+@torch.no_grad()
+def class_similarity(vis_feat: torch.Tensor, txt_feat: torch.Tensor, return_sims: bool = True, engine: FusionEngine = None):
+    """`_get_similarity` + the arg max that follows it in the reference's evaluation loops
+    (engine/distil.py:244-246,289-290, tools/validate_upper_bound.py:59-61,101-102):
+
+        txt_feat /= txt_feat.norm(dim=-1, keepdim=True)       # IN PLACE on the class table the caller passes
+        sims = vis_feat @ txt_feat.T                          # (M, K) fp32, vis_feat is NOT normalised
+        pred = torch.max(sims, 1)[1]                          # (M,) int64
+
+    One tcgen05 GEMM whose epilogue keeps each row's arg max, so the (M, K) matrix is written only when
+    `return_sims` (the reference feeds it to the cross-entropy criterion, engine/distil.py:302).
+    Returns (sims | None, pred)."""
+    if not (isinstance(vis_feat, torch.Tensor) and vis_feat.is_cuda and isinstance(txt_feat, torch.Tensor) and txt_feat.is_cuda):
+        raise RuntimeError("dropclip_b200 grounding needs CUDA tensors; there is no CPU fallback")
+    if vis_feat.dim() != 2 or txt_feat.dim() != 2 or vis_feat.shape[1] != txt_feat.shape[1]:
+        raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({tuple(vis_feat.shape)} and {tuple(txt_feat.T.shape)})")
+    txt_feat /= txt_feat.norm(dim=-1, keepdim=True)  # K x C, tiny; in place like the reference
+    eng = engine or FusionEngine(vis_feat.device)
+    x = vis_feat if vis_feat.dtype in (torch.float16, torch.float32) else vis_feat.float()
+    x = x.contiguous()
+    if x.shape[0] == 0:
+        return (torch.empty((0, txt_feat.shape[0]), dtype=torch.float32, device=x.device) if return_sims else None,
+                torch.empty(0, dtype=torch.int64, device=x.device))
+    sims, pred, _ = eng.ground(x, txt_feat, _lib.DC_GROUND_CLASS, 0.1, normalize=False, want_matrix=return_sims)
+    if sims is not None and vis_feat.dtype != torch.float32 and vis_feat.dtype == txt_feat.dtype:
+        sims = sims.to(vis_feat.dtype)
+    return sims, pred
+
+
+def _get_similarity(vis_feat, txt_feat):
+    """Name and signature of the closure in engine/distil.py:244-246 / tools/validate_upper_bound.py:59-61."""
+    return class_similarity(vis_feat, txt_feat, return_sims=True)[0]

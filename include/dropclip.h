@@ -54,7 +54,8 @@ enum dc_sim_kernel { DC_SIM_NONE = 0, DC_SIM_MAX = 1, DC_SIM_MEAN = 2 };
 enum dc_ground_mode {
   DC_GROUND_RAW = 0,    /* sims[n, p] = <x_n, t_p>                         models/similarity.py:49,67 */
   DC_GROUND_PAIRED = 1, /* paired softmax of column 0 against the others   models/similarity.py:51-61 */
-  DC_GROUND_ARGMAX = 2  /* pos - mean(neg) and (argmax == 0)               models/similarity.py:91-101 */
+  DC_GROUND_ARGMAX = 2, /* pos - mean(neg) and (argmax == 0)               models/similarity.py:91-101 */
+  DC_GROUND_CLASS = 3   /* raw sims (optional) + index of the row maximum  engine/distil.py:244-246,289-290 */
 };
 
 DC_API int dc_abi_version(void);
@@ -307,19 +308,24 @@ DC_API int dc_voxel_gather(const void* in, int64_t row_bytes, const int64_t* sam
 DC_API int dc_row_normalize(void* x, int dtype, int64_t n_rows, int dim, int normalize, void* plane_hi,
                      void* plane_lo, dc_stream_t stream);
 
-/* sims = X . T^T followed by the mode's epilogue, one tcgen05 GEMM.
+/* sims = X . T^T followed by the mode's epilogue, one tcgen05 GEMM per block of 256 prompts.
  *   x_hi/x_lo  [n_points, dim] fp16 planes (x_lo NULL for fp16 features)
- *   t_hi/t_lo  [n_prompts, dim] fp16 planes, n_prompts <= 256, prompt 0 is the positive one
+ *   t_hi/t_lo  [n_prompts, dim] fp16 planes, any n_prompts >= 1, prompt 0 is the positive one
  *   DC_GROUND_RAW:    out [n_points, out_ld] fp32 raw similarities
  *   DC_GROUND_PAIRED: out [n_points] fp32
  *   DC_GROUND_ARGMAX: out [n_points] fp32 (pos - mean(neg)), pred [n_points] uint8 (argmax == 0)
+ *   DC_GROUND_CLASS:  argmax_idx [n_points] int64 = torch.max(sims, 1)[1]; out as RAW, or NULL to skip the matrix
+ *                     (replaces _get_similarity + argmax, engine/distil.py:244-246,289-290,
+ *                     tools/validate_upper_bound.py:59-61,101-102)
  *   minmax [4] fp32: min/max of `out` values and min/max of the raw similarities (device,
  *   updated atomically; initialise with dc_ground_init_minmax).
+ *   workspace: dc_ground_workspace() bytes (0 up to 256 prompts; per-point partial results beyond).
  */
 DC_API int dc_ground_init_minmax(float* minmax, dc_stream_t stream);
+DC_API size_t dc_ground_workspace(int64_t n_points, int n_prompts, int mode);
 DC_API int dc_ground(const void* x_hi, const void* x_lo, int64_t n_points, const void* t_hi, const void* t_lo,
               int n_prompts, int dim, int mode, float softmax_temp, float* out, int out_ld, uint8_t* pred,
-              float* minmax, dc_stream_t stream);
+              int64_t* argmax_idx, float* minmax, void* workspace, size_t workspace_bytes, dc_stream_t stream);
 /* Global min-max normalisation + threshold (models/similarity.py:83-88, :95-98):
  * values <- (v - min)/(max - min) (or v / max when the raw extrema coincide), pred = values > thr
  * when pred_from_threshold != 0. */
