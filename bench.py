@@ -664,8 +664,7 @@ def other_configs(dev, eng):
         flush.zero_()  # 256 MB > L2: the features come from HBM
         a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        vals, pred, mm = eng.ground(x, t, lib_mod.DC_GROUND_PAIRED, 0.1, normalize=True)
-        eng.minmax_threshold(vals.view(-1), mm, False, 0.7, True)
+        vals, pred = eng.predict(x, t, lib_mod.DC_GROUND_PAIRED, 0.1, True, 0.7)
         e.record()
         torch.cuda.synchronize()
         if it >= 3:

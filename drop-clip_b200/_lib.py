@@ -59,7 +59,9 @@ SIGNATURES = {
     "dc_row_normalize": (c_int, [P, c_int, c_int64, c_int, c_int, P, P, P]),
     "dc_ground_init_minmax": (c_int, [P, P]),
     "dc_ground_workspace": (c_size_t, [c_int64, c_int, c_int]),
-    "dc_ground": (c_int, [P, P, c_int64, P, P, c_int, c_int, c_int, c_float, P, c_int, P, P, P, P, c_size_t, P]),
+    "dc_ground": (c_int, [P, P, c_int64, P, P, c_int, c_int, c_int, c_float, c_int, P, c_int, P, P, P, P, c_size_t, P]),
+    "dc_predict_workspace": (c_size_t, [c_int64, c_int, c_int, c_int, c_int, c_int]),
+    "dc_predict": (c_int, [P, c_int, c_int64, P, c_int, c_int, c_int, c_int, c_float, c_int, c_float, P, P, P, P, c_size_t, P]),
     "dc_minmax_threshold": (c_int, [P, c_int64, P, c_int, c_float, c_int, P, P]),
     "dc_backproject": (c_int, [P, c_int, c_int, c_int, P, c_int, c_int, P, P, P]),
     "dc_points_to_pixels": (c_int, [P, c_int64, P, P, P]),

@@ -3,6 +3,7 @@
 // Reference: utils/feature_fusion.py:311-313 (feat_v_norm @ query.T), models/similarity.py:28-101
 // (vis_feats @ text.T, paired softmax, min-max, threshold), engine/distil.py:244-246.
 #include <algorithm>
+#include <stdlib.h>
 #include <mutex>
 
 #include "gemm.cuh"
@@ -134,20 +135,55 @@ __global__ void __launch_bounds__(256) row_normalize_vec_kernel(T* __restrict__ 
     }
   }
   if (normalize) {
-    double ss = 0.0;
+    float nrm;
+    bool exact = false;
+    if (sizeof(T) == 2) {
+      // fp16 rows: the squares are exact in fp32 (11-bit significands) and every partial sum is positive, so an fp32
+      // accumulation (4 chains + 5 shuffle rounds) + sqrt stays within 20 eps = 1.2e-6 of the exact norm. If both ends of
+      // that interval round to the same fp16 value (99 % of the rows), it IS the correctly rounded norm; otherwise the
+      // fp64 accumulation below decides. (The fp64 chain on every row cost 25 % of this kernel's time.)
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < kChunks; ++k)
+      for (int k = 0; k < kChunks; ++k)
 #pragma unroll
-      for (int j = 0; j < kPer; ++j) ss = fma((double)v[k][j], (double)v[k][j], ss);
-    const float nrm = rounded_norm<T>(warp_sum_f64(ss));
+        for (int j = 0; j < kPer; ++j) s[j & 3] = fmaf(v[k][j], v[k][j], s[j & 3]);
+      const float tot = dc::warp_sum((s[0] + s[1]) + (s[2] + s[3]));
+      const float n32 = sqrtf(tot);
+      const __half lo = __float2half_rn(n32 * (1.0f - 1.5e-6f)), hi = __float2half_rn(n32 * (1.0f + 1.5e-6f));
+      nrm = __half2float(lo);
+      exact = (__half_as_ushort(lo) == __half_as_ushort(hi)) && n32 < 60000.f && tot > 1e-12f;
+    }
+    if (!exact) {
+      double ss = 0.0;
 #pragma unroll
-    for (int k = 0; k < kChunks; ++k)
+      for (int k = 0; k < kChunks; ++k)
 #pragma unroll
-      for (int j = 0; j < kPer; ++j) {
-        float q = v[k][j] / nrm;  // IEEE division, like torch
-        if (sizeof(T) == 2) q = __half2float(__float2half_rn(q));
-        v[k][j] = q;
-      }
+        for (int j = 0; j < kPer; ++j) ss = fma((double)v[k][j], (double)v[k][j], ss);
+      nrm = rounded_norm<T>(warp_sum_f64(ss));
+    }
+    if (sizeof(T) == 2 && nrm > 0.f && nrm < INFINITY) {
+      // x / nrm correctly rounded without the division sequence: with the correctly rounded reciprocal r, q = x * r, the
+      // exact remainder x - q * nrm and one fma give RN(x / nrm) (Markstein; nrm is an fp16 value, so its significand is
+      // never all ones; quotients of fp16 values never leave the fp32 normal range)
+      const float r = 1.0f / nrm;
+#pragma unroll
+      for (int k = 0; k < kChunks; ++k)
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+          const float q0 = v[k][j] * r;
+          // copysign: (+0) + (-0) = +0 in the last fma would lose the sign of a -0 entry (IEEE division keeps it)
+          v[k][j] = copysignf(__half2float(__float2half_rn(fmaf(fmaf(-q0, nrm, v[k][j]), r, q0))), v[k][j]);
+        }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kChunks; ++k)
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+          float q = v[k][j] / nrm;  // IEEE division, like torch
+          if (sizeof(T) == 2) q = __half2float(__float2half_rn(q));
+          v[k][j] = q;
+        }
+    }
   }
 #pragma unroll
   for (int k = 0; k < kChunks; ++k) {
@@ -705,6 +741,19 @@ int launch_bn(int bn, const void* a_hi, const void* a_lo, int64_t a_rows, const 
 
 int pick_bn(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
 
+// grounding GEMM with the in-place fp16 row normalisation of A fused in (p.norm_rows): k = 256 * chunks
+template <int kNormChunks>
+int launch_bn_norm(int bn, const void* a_hi, int64_t a_rows, const void* b_hi, const void* b_lo, int64_t b_rows,
+                   const Params& p, const EpiGround& epi, int max_tiles, cudaStream_t st) {
+  switch (bn) {
+    case 32: return dc::gemm::launch<32, EpiGround, kNormChunks>(a_hi, nullptr, a_rows, b_hi, b_lo, b_rows, p, epi, max_tiles, st);
+    case 64: return dc::gemm::launch<64, EpiGround, kNormChunks>(a_hi, nullptr, a_rows, b_hi, b_lo, b_rows, p, epi, max_tiles, st);
+    case 128: return dc::gemm::launch<128, EpiGround, kNormChunks>(a_hi, nullptr, a_rows, b_hi, b_lo, b_rows, p, epi, max_tiles, st);
+    case 256: return dc::gemm::launch<256, EpiGround, kNormChunks>(a_hi, nullptr, a_rows, b_hi, b_lo, b_rows, p, epi, max_tiles, st);
+  }
+  return dc::fail(DC_ERR_UNSUPPORTED, "unsupported GEMM N tile %d", bn);
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct ScoreWorkspace {
@@ -843,8 +892,8 @@ size_t dc_ground_workspace(int64_t n_points, int n_prompts, int mode) {
 }
 
 int dc_ground(const void* x_hi, const void* x_lo, int64_t n_points, const void* t_hi, const void* t_lo, int n_prompts,
-              int dim, int mode, float softmax_temp, float* out, int out_ld, uint8_t* pred, int64_t* argmax_idx,
-              float* minmax, void* workspace, size_t workspace_bytes, dc_stream_t stream) {
+              int dim, int mode, float softmax_temp, int normalize_fp16_rows, float* out, int out_ld, uint8_t* pred,
+              int64_t* argmax_idx, float* minmax, void* workspace, size_t workspace_bytes, dc_stream_t stream) {
   DC_CHECK_ARG(x_hi && t_hi && minmax, "dc_ground: null pointer argument");
   DC_CHECK_ARG(out || mode == DC_GROUND_CLASS, "dc_ground: null output");
   DC_CHECK_ARG(n_prompts >= 1, "dc_ground: at least one prompt (got %d)", n_prompts);
@@ -856,7 +905,19 @@ int dc_ground(const void* x_hi, const void* x_lo, int64_t n_points, const void* 
                "dc_ground: paired/argmax need at least one negative prompt");
   DC_CHECK_ARG((mode != DC_GROUND_RAW && mode != DC_GROUND_CLASS) || !out || out_ld >= n_prompts, "dc_ground: out_ld < n_prompts");
   DC_CHECK_ARG(n_points < (1ll << 31), "dc_ground: too many points for one call");
+  DC_CHECK_ARG(!normalize_fp16_rows || !x_lo, "dc_ground: normalize_fp16_rows is for fp16 features (x_lo must be NULL)");
   if (n_points <= 0) return DC_OK;
+  // fp16 features to be normalised in place (models/similarity.py:77): fused into the first GEMM launch when the row
+  // width allows (four extra warps normalise the rows of the coming tiles while the tensor pipe works, so the features
+  // cross HBM once in each direction instead of being re-read by the GEMM), else a separate pass first
+  // (measured on B200, 200k x 256 x 768: the fused kernel is bit-identical but not faster than the two passes - its
+  // normaliser warps are latency-bound, profiles/r02_ground_fused.md - so it is opt-in: DC_GROUND_FUSED=1)
+  const bool fuse_norm = normalize_fp16_rows && (dim == 512 || dim == 768 || dim == 1024) && ((uintptr_t)x_hi & 15) == 0 &&
+                         getenv("DC_GROUND_FUSED") && !getenv("DC_GROUND_TWO_PASS");
+  if (normalize_fp16_rows && !fuse_norm) {
+    const int rc = launch_row_normalize(const_cast<void*>(x_hi), DC_F16, n_points, dim, 1, true, nullptr, nullptr, dc::as_stream(stream));
+    if (rc) return rc;
+  }
   const size_t need = dc_ground_workspace(n_points, n_prompts, mode);
   if (need > 0 && (!workspace || workspace_bytes < need))
     return dc::fail(DC_ERR_WORKSPACE, "dc_ground: %zu workspace bytes needed for %d prompts, got %zu", need, n_prompts, workspace_bytes);
@@ -869,6 +930,8 @@ int dc_ground(const void* x_hi, const void* x_lo, int64_t n_points, const void* 
     const int cols = n_prompts - c0 < 256 ? n_prompts - c0 : 256;
     const int bn = pick_bn(cols);
     Params p{nullptr, nullptr, n_points, cols, dim, n_terms};
+    // after the separate normalisation pass the rows written last are still in L2 (126 MB): walk the tiles backwards
+    p.reverse = (normalize_fp16_rows && !fuse_norm && c0 == 0 && !getenv("DC_GROUND_FORWARD")) ? 1 : 0;
     EpiGround epi{};
     epi.mode = mode;
     epi.n_prompts = cols;
@@ -884,10 +947,70 @@ int dc_ground(const void* x_hi, const void* x_lo, int64_t n_points, const void* 
     epi.argmax_idx = argmax_idx;
     const char* th = (const char*)t_hi + (size_t)c0 * dim * 2;
     const char* tl = t_lo ? (const char*)t_lo + (size_t)c0 * dim * 2 : th;
-    const int rc = launch_bn(bn, x_hi, x_lo, n_points, th, tl, cols, p, epi, max_tiles, dc::as_stream(stream));
+    int rc;
+    if (fuse_norm && c0 == 0) {
+      p.norm_rows = reinterpret_cast<__half*>(const_cast<void*>(x_hi));
+      rc = dim == 512 ? launch_bn_norm<2>(bn, x_hi, n_points, th, tl, cols, p, epi, max_tiles, dc::as_stream(stream))
+         : dim == 768 ? launch_bn_norm<3>(bn, x_hi, n_points, th, tl, cols, p, epi, max_tiles, dc::as_stream(stream))
+                      : launch_bn_norm<4>(bn, x_hi, n_points, th, tl, cols, p, epi, max_tiles, dc::as_stream(stream));
+    } else {
+      rc = launch_bn(bn, x_hi, x_lo, n_points, th, tl, cols, p, epi, max_tiles, dc::as_stream(stream));
+    }
     if (rc) return rc;
   }
   return DC_OK;
+}
+
+size_t dc_predict_workspace(int64_t n_points, int n_prompts, int dim, int feat_dtype, int text_dtype, int mode) {
+  size_t b = 256;  // minmax
+  if (text_dtype == DC_F32) b += 2 * align_up((size_t)n_prompts * dim * 2, 256);
+  if (feat_dtype == DC_F32) b += 2 * align_up((size_t)(n_points > 0 ? n_points : 1) * dim * 2, 256);
+  b += align_up(dc_ground_workspace(n_points, n_prompts, mode), 256);
+  return b;
+}
+
+int dc_predict(void* feats, int feat_dtype, int64_t n_points, const void* text, int text_dtype, int n_prompts, int dim,
+               int mode, float softmax_temp, int normalize, float threshold, float* out, uint8_t* pred, float** minmax_out,
+               void* workspace, size_t workspace_bytes, dc_stream_t stream) {
+  DC_CHECK_ARG(feats && text && out && pred && workspace, "dc_predict: null pointer argument");
+  DC_CHECK_ARG(feat_dtype == DC_F16 || feat_dtype == DC_F32, "dc_predict: features must be fp16 or fp32");
+  DC_CHECK_ARG(text_dtype == DC_F16 || text_dtype == DC_F32, "dc_predict: prompt embeddings must be fp16 or fp32");
+  DC_CHECK_ARG(mode == DC_GROUND_RAW || mode == DC_GROUND_PAIRED || mode == DC_GROUND_ARGMAX, "dc_predict: bad mode");
+  DC_CHECK_ARG(mode != DC_GROUND_RAW || n_prompts == 1, "dc_predict: raw mode is the no-negatives case (one prompt)");
+  DC_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "dc_predict: workspace must be 256-byte aligned");
+  const size_t need = dc_predict_workspace(n_points, n_prompts, dim, feat_dtype, text_dtype, mode);
+  if (workspace_bytes < need) return dc::fail(DC_ERR_WORKSPACE, "dc_predict: workspace %zu < %zu", workspace_bytes, need);
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  float* minmax = reinterpret_cast<float*>(w);
+  w += 256;
+  if (minmax_out) *minmax_out = minmax;
+  int rc;
+  if ((rc = dc_ground_init_minmax(minmax, stream))) return rc;
+  if (n_points <= 0) return DC_OK;
+  const void *t_hi = text, *t_lo = nullptr;
+  if (text_dtype == DC_F32) {  // fp16 hi + lo planes of the (already normalised) prompt rows; fp16 prompts are used as they are
+    const size_t pb = align_up((size_t)n_prompts * dim * 2, 256);
+    if ((rc = launch_row_normalize(const_cast<void*>(text), DC_F32, n_prompts, dim, 0, false, w, w + pb, dc::as_stream(stream)))) return rc;
+    t_hi = w;
+    t_lo = w + pb;
+    w += 2 * pb;
+  }
+  const void *x_hi = feats, *x_lo = nullptr;
+  if (feat_dtype == DC_F32) {
+    const size_t xb = align_up((size_t)n_points * dim * 2, 256);
+    if ((rc = launch_row_normalize(feats, DC_F32, n_points, dim, normalize, true, w, w + xb, dc::as_stream(stream)))) return rc;
+    x_hi = w;
+    x_lo = w + xb;
+    w += 2 * xb;
+  }
+  if ((rc = dc_ground(x_hi, x_lo, n_points, t_hi, t_lo, n_prompts, dim, mode, softmax_temp,
+                      (feat_dtype == DC_F16 && normalize) ? 1 : 0, out, mode == DC_GROUND_RAW ? n_prompts : 1, pred, nullptr,
+                      minmax, w, dc_ground_workspace(n_points, n_prompts, mode), stream)))
+    return rc;
+  // global min-max (+ threshold) of models/similarity.py:83-88; argmax branch :95-98 normalises pos - mean(neg) and keeps
+  // the arg-max prediction the epilogue wrote
+  return dc_minmax_threshold(out, n_points, minmax, mode == DC_GROUND_ARGMAX ? 1 : 0, threshold,
+                             mode == DC_GROUND_ARGMAX ? 0 : 1, pred, stream);
 }
 
 int dc_minmax_threshold(float* values, int64_t n, const float* minmax, int use_raw_extrema_for_test, float threshold,

@@ -745,9 +745,7 @@ class FusionEngine:
             x_hi, x_lo = planes[0], planes[1]
             check(self.lib.dc_row_normalize(ptr(feats), code, n, dim, int(normalize), ptr(x_hi), ptr(x_lo), current_stream()))
         else:
-            if normalize:
-                check(self.lib.dc_row_normalize(ptr(feats), code, n, dim, 1, None, None, current_stream()))
-            x_hi, x_lo = feats, None
+            x_hi, x_lo = feats, None  # fp16 rows are normalised in place inside dc_ground (fused into the GEMM kernel)
         t32 = text.to(torch.float32).contiguous()
         tplanes = torch.empty((2, p, dim), dtype=torch.float16, device=dev)
         t_lo = tplanes[1] if text.dtype == torch.float32 else None
@@ -768,9 +766,32 @@ class FusionEngine:
         ws_bytes = self.lib.dc_ground_workspace(n, p, mode)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
         check(self.lib.dc_ground(ptr(x_hi), ptr(x_lo), n, ptr(tplanes[0]), ptr(t_lo), p, dim, mode, float(softmax_temp),
-                                 ptr(out), ld, ptr(pred), ptr(argmax_idx), ptr(minmax), ptr(ws), ws_bytes, current_stream()))
+                                 int(bool(normalize) and not is_f32), ptr(out), ld, ptr(pred), ptr(argmax_idx), ptr(minmax),
+                                 ptr(ws), ws_bytes, current_stream()))
         self.launches += 3 + (p + 255) // 256
         return out, (argmax_idx if mode == _lib.DC_GROUND_CLASS else pred), minmax
+
+    def predict(self, feats: torch.Tensor, text: torch.Tensor, mode: int, softmax_temp: float, normalize: bool, threshold: float):
+        """ClipSimilarity.predict after the text tower (models/similarity.py:77-101) in one library call and two
+        allocations: returns (score (N,) fp32 min-max normalised, pred (N,) uint8). `feats` is normalised in place."""
+        n, dim = feats.shape
+        p = int(text.shape[0])
+        dev = feats.device
+        text = text.contiguous()
+        if text.dtype not in (torch.float16, torch.float32):
+            text = text.float()
+        fcode, tcode = _lib.torch_dtype_code(feats.dtype), _lib.torch_dtype_code(text.dtype)
+        ws_bytes = self.lib.dc_predict_workspace(n, p, dim, fcode, tcode, mode)
+        res = torch.empty(max(n, 1) * 5 + 256, dtype=torch.uint8, device=dev)  # score fp32 + pred u8 in one allocation
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        shift = (-ws.data_ptr()) % 256
+        out = res[:4 * n].view(torch.float32)
+        pred = res[4 * max(n, 1):4 * max(n, 1) + n]
+        check(self.lib.dc_predict(ptr(feats), fcode, n, ptr(text), tcode, p, dim, mode, float(softmax_temp), int(bool(normalize)),
+                                  float(threshold), ctypes.c_void_p(res.data_ptr()), ctypes.c_void_p(res.data_ptr() + 4 * max(n, 1)),
+                                  None, ctypes.c_void_p(ws.data_ptr() + shift), ws_bytes, current_stream()))
+        self.launches += 3 + int(tcode == _lib.DC_F32) + int(fcode == _lib.DC_F32 or bool(normalize)) + (p + 255) // 256 - 1
+        return out, pred
 
     def minmax_threshold(self, values, minmax, use_raw: bool, threshold: float, want_pred: bool):
         pred = torch.empty(values.numel(), dtype=torch.uint8, device=values.device) if want_pred else None

@@ -112,19 +112,16 @@ class ClipSimilarity(object):
         n = vis_feats.shape[0]
         if qneg is None or (qneg is not None and method == "paired"):
             mode = _lib.DC_GROUND_RAW if qn is None else _lib.DC_GROUND_PAIRED
-            out, _, mm = eng.ground(vis_feats, text, mode, self.SOFTMAX_TEMP, normalize=bool(norm_vis_feat))
-            out = out.view(-1)
-            pred = eng.minmax_threshold(out, mm, False, threshold, True)
-            pred, sims = pred.bool(), out
+            sims, pred = eng.predict(vis_feats, text, mode, self.SOFTMAX_TEMP, bool(norm_vis_feat), threshold)
+            pred = pred.view(torch.bool)
             if n == 1:  # .squeeze() in the reference makes these 0-d (quirk q18)
                 pred, sims = pred.reshape(()), sims.reshape(())
             return pred, sims
         elif qneg is not None and method == "argmax":
             if n == 1:
                 raise IndexError("too many indices for tensor of dimension 1")  # reference behaviour (q18)
-            out, pred, mm = eng.ground(vis_feats, text, _lib.DC_GROUND_ARGMAX, self.SOFTMAX_TEMP, normalize=bool(norm_vis_feat))
-            eng.minmax_threshold(out, mm, True, threshold, False)
-            return pred.bool(), out
+            out, pred = eng.predict(vis_feats, text, _lib.DC_GROUND_ARGMAX, self.SOFTMAX_TEMP, bool(norm_vis_feat), threshold)
+            return pred.view(torch.bool), out
 
 
 # ---------------------------------------------------------------------- a18

@@ -320,12 +320,29 @@ DC_API int dc_row_normalize(void* x, int dtype, int64_t n_rows, int dim, int nor
  *   minmax [4] fp32: min/max of `out` values and min/max of the raw similarities (device,
  *   updated atomically; initialise with dc_ground_init_minmax).
  *   workspace: dc_ground_workspace() bytes (0 up to 256 prompts; per-point partial results beyond).
+ *   normalize_fp16_rows != 0 (fp16 features only, x_lo NULL): x_hi is L2-normalised IN PLACE first with torch's fp16
+ *   semantics (models/similarity.py:77, quirk q15) - inside the GEMM kernel for dim 512/768/1024 (extra warps normalise the
+ *   rows of the coming tiles, the A-operand TMA loads then hit L2), by a separate pass otherwise.
  */
 DC_API int dc_ground_init_minmax(float* minmax, dc_stream_t stream);
 DC_API size_t dc_ground_workspace(int64_t n_points, int n_prompts, int mode);
 DC_API int dc_ground(const void* x_hi, const void* x_lo, int64_t n_points, const void* t_hi, const void* t_lo,
-              int n_prompts, int dim, int mode, float softmax_temp, float* out, int out_ld, uint8_t* pred,
-              int64_t* argmax_idx, float* minmax, void* workspace, size_t workspace_bytes, dc_stream_t stream);
+              int n_prompts, int dim, int mode, float softmax_temp, int normalize_fp16_rows, float* out, int out_ld,
+              uint8_t* pred, int64_t* argmax_idx, float* minmax, void* workspace, size_t workspace_bytes,
+              dc_stream_t stream);
+/* ClipSimilarity.predict after the text tower (models/similarity.py:77-101) as ONE call: init of the extrema, operand
+ * planes, in-place normalisation of the features (`normalize`), GEMM + epilogue, global min-max and threshold - four to
+ * six launches back to back without returning to the host in between.
+ *   feats [n_points, dim] fp16/fp32 (normalised in place when `normalize`), text [n_prompts, dim] fp16/fp32 rows already
+ *   L2-normalised, prompt 0 positive; mode RAW (no negatives: n_prompts == 1), PAIRED or ARGMAX.
+ *   out [n_points] fp32 = the min-max normalised score, pred [n_points] uint8 (score > threshold, or argmax == 0).
+ *   *minmax_out (host pointer, optional) receives the device address of the four extrema inside the workspace.
+ *   workspace: 256-byte aligned, dc_predict_workspace() bytes. */
+DC_API size_t dc_predict_workspace(int64_t n_points, int n_prompts, int dim, int feat_dtype, int text_dtype, int mode);
+DC_API int dc_predict(void* feats, int feat_dtype, int64_t n_points, const void* text, int text_dtype, int n_prompts, int dim,
+               int mode, float softmax_temp, int normalize, float threshold, float* out, uint8_t* pred,
+               float** minmax_out, void* workspace, size_t workspace_bytes, dc_stream_t stream);
+
 /* Global min-max normalisation + threshold (models/similarity.py:83-88, :95-98):
  * values <- (v - min)/(max - min) (or v / max when the raw extrema coincide), pred = values > thr
  * when pred_from_threshold != 0. */

@@ -109,3 +109,78 @@ def test_more_than_256_prompts(n_prompts):
     top2 = torch.topk(rs, 2, dim=1).values
     sure = (top2[:, 0] - top2[:, 1]) > 1e-4
     assert torch.equal(idx.cpu()[sure], rs.argmax(1)[sure])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [512, 768, 1024])
+def test_fused_row_normalisation_equals_the_separate_pass(dim):
+    """predict() normalises fp16 features in place (models/similarity.py:77). The normalisation fused into the GEMM
+    kernel (extra warps working ahead of the TMA producer) must leave exactly the bytes the separate pass leaves, and
+    give exactly the same similarities, for full tiles, ragged tails and row counts below one tile."""
+    import os
+    from dropclip_b200 import _lib
+    from dropclip_b200.engine import FusionEngine
+    eng = FusionEngine("cuda")
+    g = torch.Generator(device="cuda").manual_seed(dim)
+    for n, p in ((1, 5), (31, 40), (127, 5), (128, 256), (129, 33), (1000, 256), (70_001, 200)):
+        x0 = (torch.randn((n, dim), generator=g, device="cuda") * 3).half()
+        t = torch.randn((p, dim), generator=g, device="cuda")
+        t = (t / t.norm(dim=-1, keepdim=True)).half()
+        res = {}
+        for name, env in (("fused", "DC_GROUND_FUSED"), ("two_pass", "DC_GROUND_TWO_PASS")):
+            os.environ.pop("DC_GROUND_TWO_PASS", None)
+            os.environ.pop("DC_GROUND_FUSED", None)
+            os.environ[env] = "1"
+            try:
+                outs = []
+                for mode in (_lib.DC_GROUND_PAIRED, _lib.DC_GROUND_ARGMAX, _lib.DC_GROUND_RAW):
+                    x = x0.clone()
+                    out, pred, mm = eng.ground(x, t, mode, 0.1, normalize=True)
+                    torch.cuda.synchronize()
+                    outs.append((x, out, pred, mm))
+                res[name] = outs
+            finally:
+                os.environ.pop("DC_GROUND_TWO_PASS", None)
+                os.environ.pop("DC_GROUND_FUSED", None)
+        for (xa, oa, pa, ma), (xb, ob, pb, mb) in zip(res["fused"], res["two_pass"]):
+            assert torch.equal(xa.view(torch.int16), xb.view(torch.int16)), (n, p, "normalised rows differ")
+            assert torch.equal(oa, ob) and torch.equal(ma, mb), (n, p)
+            assert (pa is None and pb is None) or torch.equal(pa, pb)
+        ref = x0.float()
+        ref = (ref / ref.norm(dim=-1, keepdim=True).half().float()).half()
+        assert (res["fused"][0][0].float() - ref.float()).abs().max().item() <= 2e-3  # torch's own fp16 result, to an ulp
+
+
+@pytest.mark.gpu
+def test_fp16_row_normalisation_is_the_correctly_rounded_one():
+    """In-place normalisation of fp16 features (models/similarity.py:77: `x /= x.norm(dim=-1, keepdim=True)`): the kernel's
+    fp32 fast path with its exactness test and fp64 fall-back must give, for EVERY row, the correctly rounded fp16 norm and
+    the fp16-rounded IEEE quotient - checked against an fp64 evaluation in torch, including rows whose norm sits next to an
+    fp16 rounding boundary, zero rows, tiny and huge rows."""
+    from dropclip_b200 import _lib
+    from dropclip_b200.engine import FusionEngine
+    eng = FusionEngine("cuda")
+    g = torch.Generator(device="cuda").manual_seed(77)
+    n, c = 120_000, 768
+    x = (torch.randn((n, c), generator=g, device="cuda") * torch.rand((n, 1), generator=g, device="cuda") * 4).half()
+    x[5] = 0
+    x[6] = 6e-8     # subnormal fp16 entries
+    x[7] = 2000.0   # norm overflows fp16 -> inf -> rows of zeros, like torch
+    # rows engineered onto a rounding boundary of the norm: one large entry, the rest zero => norm = |entry| exactly
+    x[8] = 0
+    x[8, 3] = 1.0009765625
+    d = x.double().pow(2).sum(-1, keepdim=True).sqrt()                     # fp64 error << fp16 spacing
+    # correctly rounded fp16 of d. (d.half() goes through fp32 in torch - a double rounding that lands on the wrong
+    # neighbour for ~1 row in 10^4 -, so the nearest of the three candidate fp16 values is picked in fp64.)
+    h0 = d.float().half()
+    bits = h0.view(torch.int16)
+    cands = torch.stack([h0, (bits + 1).view(torch.float16), (bits - 1).clamp_min(0).view(torch.float16)], 0)
+    pick = (cands.double() - d).abs().nan_to_num(nan=float("inf")).argmin(0, keepdim=True)
+    want_nrm = torch.where(torch.isfinite(h0) & (h0 > 0), cands.gather(0, pick)[0], h0)
+    want = (x.float() / want_nrm.float()).half()                            # IEEE fp32 division, rounded to fp16
+    y = x.clone()
+    t = torch.randn((4, c), generator=g, device="cuda").half()
+    eng.ground(y, t, _lib.DC_GROUND_RAW, 0.1, normalize=True)
+    torch.cuda.synchronize()
+    same = (y.view(torch.int16) == want.view(torch.int16)) | (torch.isnan(y) & torch.isnan(want))
+    assert bool(same.all()), f"{int((~same).any(-1).sum())} rows differ"
