@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace {
 
@@ -650,6 +651,597 @@ __global__ void __launch_bounds__(kThreads) view_clip_gather_kernel(const double
   }
 }
 
+
+// =====================================================================================================================
+// Pixel-level fusion on the tensor cores (tcgen05).
+//
+// The 16-tap bicubic fold of one visible (point, view) pair is a 16 x C contraction: f = sum_t w_t T_t. Pairs that
+// share a bicubic FOOTPRINT - the same view and the same first source cell (iy0, ix0), (ph + 1)(pw + 1) = 825 of them per
+// view at 24 x 32 - share their 16 taps, so the pairs are counting-sorted by (view, footprint) and every 128 consecutive
+// sorted pairs become one MMA tile:
+//     D[128 pairs x C] = sum over the footprint segments g of the tile   A_g[128 x 16] . B_g[16 x C]
+// A_g holds the pairs' 16 tap weights (zero rows outside segment g), B_g the segment's taps. fp32 accuracy on the fp16
+// tensor path comes from hi/lo planes (A_hi.B_hi + A_hi.B_lo + A_lo.B_hi), as in gemm.cuh. B_g is an MN-major operand
+// (taps are rows of C contiguous channels in memory) in the no-swizzle core-matrix layout, filled with 16-byte cp.async;
+// A_g is K-major, written from registers. C is walked in 256-column chunks with two TMEM accumulators in flight.
+// Pass NORM (only under norm_feat): the epilogue reduces sum f^2 per pair. A warp-per-pair kernel then evaluates the
+// similarity weight (fp64 chain of finish_weight) and the pair's scale = weight / |f|. Pass ACCUM: the epilogue scales
+// the row and adds it to the point's output row with red.global.add.v4.f32 (rows of one point come from different tiles;
+// the order of the additions is not fixed, the sums differ from a view-ordered sum by fp32 rounding only).
+// =====================================================================================================================
+inline int query_stride_(int max_queries) { return (max_queries + 3) & ~3; }
+
+namespace mma {
+
+using namespace dc::umma;
+
+constexpr int kStages = 3;
+constexpr int kABytes = 4096;    // one plane of A: [2 k-halves][16 row groups][8 rows][16 B]
+constexpr int kBBytes = 8192;    // one plane of B: [2 k-groups][32 column groups][8 taps][16 B]   (N = 256)
+constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+constexpr int kLoaderThreads = 128;
+constexpr int kMmaWarp = 4;
+constexpr int kEpiWarp0 = 8;
+constexpr int kThreadsMma = 384;
+constexpr int kSmemBytes = kStages * kStageBytes + 128 /*align*/ + 512 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue transposition*/;
+
+struct Footprints {
+  int ph, pw, height, width;
+  __host__ __device__ int per_view() const { return (ph + 1) * (pw + 1); }
+};
+
+// first source cell of the bicubic footprint of destination pixel `dst` (ATen: floor(scale * (dst + 0.5) - 0.5)), in [-1, in - 1]
+__device__ __forceinline__ int first_cell(int dst, int in_size, int out_size) {
+  const double src = ((double)in_size / (double)out_size) * ((double)dst + 0.5) - 0.5;
+  return (int)floor(src);
+}
+__device__ __forceinline__ int footprint_of(const Footprints& f, int pu, int pv) {
+  return (first_cell(pv, f.ph, f.height) + 1) * (f.pw + 1) + (first_cell(pu, f.pw, f.width) + 1);
+}
+
+// the projection of visibility.cu / pixel_fuse_tile_kernel (the pair is visible, hence inside the image)
+__device__ __forceinline__ void project_pixel(const double* __restrict__ m, const double* __restrict__ K, double x, double y,
+                                              double z, int& pu, int& pv) {
+  double cx = __dadd_rn(m[3], __fma_rn(m[2], z, __fma_rn(m[1], y, __dmul_rn(m[0], x))));
+  double cy = __dadd_rn(m[7], __fma_rn(m[6], z, __fma_rn(m[5], y, __dmul_rn(m[4], x))));
+  double cz = __dadd_rn(m[11], __fma_rn(m[10], z, __fma_rn(m[9], y, __dmul_rn(m[8], x))));
+  cy = -cy;
+  cz = -cz;
+  const double qx = __fma_rn(K[2], cz, __fma_rn(K[1], cy, __dmul_rn(K[0], cx)));
+  const double qy = __fma_rn(K[5], cz, __fma_rn(K[4], cy, __dmul_rn(K[3], cx)));
+  const double qz = __fma_rn(K[8], cz, __fma_rn(K[7], cy, __dmul_rn(K[6], cx)));
+  pu = 0;
+  pv = 0;
+  if (qz != 0.0) {
+    pu = (int)__ddiv_rn(qx, qz);
+    pv = (int)__ddiv_rn(qy, qz);
+  }
+}
+
+// thread per point, loop over the scene's views: pixel of every visible pair (stashed in mask layout) and the histogram
+// of (global view, footprint) keys
+__global__ void __launch_bounds__(kThreads) pair_count_kernel(PixParams p, Footprints fp, uint32_t* __restrict__ pix,
+                                                              unsigned* __restrict__ counts) {
+  const int scene = blockIdx.y;
+  const int64_t p0 = p.point_off[scene], n_pts = p.point_off[scene + 1] - p0;
+  const int64_t v0 = p.view_off[scene];
+  const int n_views = (int)(p.view_off[scene + 1] - v0);
+  const uint8_t* vis = p.visible + p.mask_off[scene];
+  uint32_t* px = pix + p.mask_off[scene];
+  double K[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) K[e] = __ldg(p.intrinsics + (int64_t)scene * 9 + e);
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_pts; i += (int64_t)gridDim.x * kThreads) {
+    const double x = __ldg(p.points + 3 * (p0 + i)), y = __ldg(p.points + 3 * (p0 + i) + 1), z = __ldg(p.points + 3 * (p0 + i) + 2);
+    for (int v = 0; v < n_views; ++v) {
+      if (!vis[(int64_t)v * n_pts + i]) continue;
+      double m[12];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) m[e] = __ldg(p.inv_poses + (v0 + v) * 16 + e);
+      int pu, pv;
+      project_pixel(m, K, x, y, z, pu, pv);
+      px[(int64_t)v * n_pts + i] = (uint32_t)pu | ((uint32_t)pv << 16);
+      atomicAdd(counts + (v0 + v) * fp.per_view() + footprint_of(fp, pu, pv), 1u);
+    }
+  }
+}
+
+// exclusive scan of `n` counters (three launches): per-block sums, scan of the block sums by one CTA, local scans + bases.
+constexpr int kScanBlock = 1024;
+__global__ void __launch_bounds__(kScanBlock) scan_sums_kernel(const unsigned* __restrict__ in, int64_t n, unsigned* __restrict__ sums) {
+  __shared__ unsigned s_w[32];
+  const int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  unsigned v = i < n ? in[i] : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned t = s_w[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) sums[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(kScanBlock) scan_bases_kernel(unsigned* __restrict__ sums, int64_t n_blocks, unsigned* __restrict__ total) {
+  __shared__ unsigned s_w[32];
+  __shared__ unsigned s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t b0 = 0; b0 < n_blocks; b0 += kScanBlock) {
+    const int64_t i = b0 + threadIdx.x;
+    const unsigned v = i < n_blocks ? sums[i] : 0u;
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += up;
+    }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const unsigned t = s_w[threadIdx.x];
+      unsigned ti = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, ti, o);
+        if (threadIdx.x >= o) ti += up;
+      }
+      s_w[threadIdx.x] = ti - t;
+    }
+    __syncthreads();
+    const unsigned base = s_carry + s_w[threadIdx.x >> 5];
+    if (i < n_blocks) sums[i] = base + incl - v;
+    __syncthreads();
+    if (threadIdx.x == kScanBlock - 1) s_carry = base + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_carry;
+}
+__global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(unsigned* __restrict__ data, int64_t n, const unsigned* __restrict__ bases) {
+  __shared__ unsigned s_w[32];
+  const int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  const unsigned v = i < n ? data[i] : 0u;
+  unsigned incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += up;
+  }
+  if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const unsigned t = s_w[threadIdx.x];
+    unsigned ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned up = __shfl_up_sync(0xffffffffu, ti, o);
+      if (threadIdx.x >= o) ti += up;
+    }
+    s_w[threadIdx.x] = ti - t;
+  }
+  __syncthreads();
+  if (i < n) data[i] = bases[blockIdx.x] + s_w[threadIdx.x >> 5] + incl - v;
+}
+
+// sorted pair records: global point index, packed pixel, key; and the pair's 16 tap weights as fp16 hi/lo planes
+// (w_t = wy[ty] * wx[tx] from the fp64 coefficients of cubic_weights64, t = 4 ty + tx)
+__global__ void __launch_bounds__(kThreads) pair_scatter_kernel(PixParams p, Footprints fp, const uint32_t* __restrict__ pix,
+                                                                unsigned* __restrict__ cursor, int* __restrict__ rec_point,
+                                                                uint32_t* __restrict__ rec_pix, int* __restrict__ rec_key,
+                                                                __half* __restrict__ arec) {
+  const int scene = blockIdx.y;
+  const int64_t p0 = p.point_off[scene], n_pts = p.point_off[scene + 1] - p0;
+  const int64_t v0 = p.view_off[scene];
+  const int n_views = (int)(p.view_off[scene + 1] - v0);
+  const uint8_t* vis = p.visible + p.mask_off[scene];
+  const uint32_t* px = pix + p.mask_off[scene];
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_pts; i += (int64_t)gridDim.x * kThreads) {
+    for (int v = 0; v < n_views; ++v) {
+      if (!vis[(int64_t)v * n_pts + i]) continue;
+      const uint32_t pp = px[(int64_t)v * n_pts + i];
+      const int pu = (int)(pp & 0xffffu), pv = (int)(pp >> 16);
+      const int key = (int)((v0 + v) * fp.per_view() + footprint_of(fp, pu, pv));
+      const unsigned pos = atomicAdd(cursor + key, 1u);
+      rec_point[pos] = (int)(p0 + i);
+      rec_pix[pos] = pp;
+      rec_key[pos] = key;
+      double wy[4], wx[4];
+      cubic_weights64(pv, fp.ph, fp.height, wy);
+      cubic_weights64(pu, fp.pw, fp.width, wx);
+      __half hi[16], lo[16];
+#pragma unroll
+      for (int ty = 0; ty < 4; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < 4; ++tx) {
+          const float w = (float)(wy[ty] * wx[tx]);
+          const __half h = __float2half_rn(w);
+          hi[ty * 4 + tx] = h;
+          lo[ty * 4 + tx] = __float2half_rn(w - __half2float(h));
+        }
+      int4* dst = reinterpret_cast<int4*>(arec + (int64_t)pos * 32);
+      dst[0] = reinterpret_cast<const int4*>(hi)[0];
+      dst[1] = reinterpret_cast<const int4*>(hi)[1];
+      dst[2] = reinterpret_cast<const int4*>(lo)[0];
+      dst[3] = reinterpret_cast<const int4*>(lo)[1];
+    }
+  }
+}
+
+// ---- descriptors (cute/atom/mma_traits_sm100.hpp documents the canonical layouts; no-swizzle = "INTERLEAVE")
+// K-major, no swizzle:  ((8, m), (8, 2)) : ((16 B, SBO), (1 elem, LBO))  - 8 x 16 B core matrices, SBO between row groups,
+//                       LBO between the two k-halves.        MN-major, no swizzle: ((8, m), (8, k)) : ((1 elem, SBO), (16 B, LBO))
+__device__ __forceinline__ uint64_t smem_desc_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;  // version
+  return d;                // layout type 0 = no swizzle
+}
+// fp32 accumulator, fp16 A (K-major) and B (MN-major: bit 16)
+__host__ __device__ constexpr uint32_t idesc_f16_f32_bmn(int m, int n) {
+  return (1u << 4) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct MmaParams {
+  const int* rec_point;
+  const int* rec_key;
+  const __half* arec;       // [pairs][32]: 16 hi, 16 lo
+  const __half* plane_hi;   // [total_views * ph * pw][dim]
+  const __half* plane_lo;
+  const unsigned* n_pairs;  // device scalar
+  int ph, pw, dim, nfp;     // nfp = footprints per view
+  float* norm2;             // [pairs]  (pass NORM)
+  const float* scale;       // [pairs]  (pass ACCUM)
+  float* out;               // [total_points][dim]
+};
+
+template <bool kAccum>
+__global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((128u - (raw_addr & 127u)) & 127u);
+  uint8_t* stages = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;                 // [kStages]  128 loader arrivals
+  uint64_t* empty = bars + kStages;      // [kStages]  MMA commit
+  uint64_t* tmem_full = bars + 2 * kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]  4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  unsigned* s_mask = reinterpret_cast<unsigned*>(tmem_slot + 2);  // [2 tile slots][4 warps]
+  int* s_nseg = reinterpret_cast<int*>(s_mask + 8);               // [2]
+  float* s_trans = reinterpret_cast<float*>(smem + kStages * kStageBytes + 512);  // [4 epilogue warps][32][36] transposition blocks
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned n_pairs = *p.n_pairs;
+  const int n_tiles = (int)((n_pairs + 127u) / 128u);
+  const int n_chunks = p.dim / 256;
+  const int ncell = p.ph * p.pw;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full + s, kLoaderThreads);
+      mbar_init(empty + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full + a, 1);
+      mbar_init(tmem_empty + a, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== loaders: thread r <-> row r of the tile =====================
+    const int r = threadIdx.x;
+    int stage = 0;
+    uint32_t phase = 0;
+    int pending = -1;  // stage whose cp.async group is in flight (lookahead of one stage)
+    int local_tile = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local_tile) {
+      const int slot = local_tile & 1;
+      const unsigned row = (unsigned)tile * 128u + (unsigned)r;
+      const bool valid = row < n_pairs;
+      const int key = valid ? __ldg(p.rec_key + row) : -1;
+      const int prev = (r == 0 || !valid) ? -2 : __ldg(p.rec_key + row - 1);
+      const unsigned starts = __ballot_sync(0xffffffffu, valid && key != prev);
+      int4 a_hi0 = make_int4(0, 0, 0, 0), a_hi1 = a_hi0, a_lo0 = a_hi0, a_lo1 = a_hi0;
+      if (valid) {
+        const int4* ar = reinterpret_cast<const int4*>(p.arec + (int64_t)row * 32);
+        a_hi0 = __ldg(ar);
+        a_hi1 = __ldg(ar + 1);
+        a_lo0 = __ldg(ar + 2);
+        a_lo1 = __ldg(ar + 3);
+      }
+      if (lane == 0) s_mask[slot * 4 + warp] = starts;
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      unsigned m[4];
+      int nseg = 0;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        m[w] = s_mask[slot * 4 + w];
+        nseg += __popc(m[w]);
+      }
+      if (r == 0) s_nseg[slot] = nseg;  // read by the MMA warp after the first full barrier of this tile
+      const int n_rows = (int)min(128u, n_pairs - (unsigned)tile * 128u);
+      for (int c = 0; c < n_chunks; ++c) {
+        int w = 0;
+        unsigned bits = m[0];
+        int seg_start = -1;
+        // walk the segment starts in row order; the segment [seg_start, next start) is emitted when its end is known
+        for (;;) {
+          int next;
+          while (w < 4 && bits == 0) { ++w; bits = w < 4 ? m[w] : 0u; }
+          if (w < 4) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            next = w * 32 + b;
+          } else {
+            next = n_rows;
+          }
+          if (seg_start >= 0) {
+            const int seg_end = next;
+            const int seg_key = __ldg(p.rec_key + (int64_t)tile * 128 + seg_start);
+            uint8_t* st = stages + stage * kStageBytes;
+            mbar_wait(empty + stage, phase ^ 1);
+            // A: my row's 16 weights, or zeros outside the segment
+            const bool mine = r >= seg_start && r < seg_end;
+            const int4 z = make_int4(0, 0, 0, 0);
+            uint8_t* arow = st + (r >> 3) * 128 + (r & 7) * 16;
+            *reinterpret_cast<int4*>(arow) = mine ? a_hi0 : z;
+            *reinterpret_cast<int4*>(arow + 2048) = mine ? a_hi1 : z;
+            *reinterpret_cast<int4*>(arow + kABytes) = mine ? a_lo0 : z;
+            *reinterpret_cast<int4*>(arow + kABytes + 2048) = mine ? a_lo1 : z;
+            // B: 16 taps x 256 channels of both planes, 16 bytes per copy
+            const int v_glob = seg_key / p.nfp, f = seg_key - v_glob * p.nfp;
+            const int iy0 = f / (p.pw + 1) - 1, ix0 = f - (f / (p.pw + 1)) * (p.pw + 1) - 1;
+            uint8_t* bh = st + 2 * kABytes;
+            uint8_t* bl = bh + kBBytes;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int idx = r + 128 * j;
+              const int t = idx >> 5, g8 = idx & 31;
+              const int cy = min(max(iy0 - 1 + (t >> 2), 0), p.ph - 1), cx = min(max(ix0 - 1 + (t & 3), 0), p.pw - 1);
+              const int64_t src = ((int64_t)v_glob * ncell + cy * p.pw + cx) * p.dim + c * 256 + g8 * 8;
+              const int dst = (t >> 3) * 4096 + g8 * 128 + (t & 7) * 16;
+              cp_async16(bh + dst, p.plane_hi + src);
+              cp_async16(bl + dst, p.plane_lo + src);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (pending >= 0) {  // the previous stage's copies have landed: publish it to the async proxy (MMA)
+              asm volatile("cp.async.wait_group 1;" ::: "memory");
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              mbar_arrive(full + pending);
+            }
+            pending = stage;
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          if (next >= n_rows) break;
+          seg_start = next;
+        }
+      }
+    }
+    if (pending >= 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(full + pending);
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_f16_f32_bmn(128, 256);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      int local_tile = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local_tile) {
+        int nseg = 1;
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+          fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+          for (int g = 0; g < nseg; ++g) {
+            mbar_wait(full + stage, phase);
+            fence_after_sync();
+            if (c == 0 && g == 0) nseg = *reinterpret_cast<volatile int*>(s_nseg + (local_tile & 1));
+            const uint32_t a_hi = smem_u32(stages + stage * kStageBytes), a_lo = a_hi + kABytes;
+            const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + kBBytes;
+            const uint64_t da_hi = smem_desc_noswizzle(a_hi, 2048, 128), da_lo = smem_desc_noswizzle(a_lo, 2048, 128);
+            const uint64_t db_hi = smem_desc_noswizzle(b_hi, 4096, 128), db_lo = smem_desc_noswizzle(b_lo, 4096, 128);
+            mma_f16_ss(d_tmem, da_hi, db_hi, idesc, g ? 1u : 0u);
+            mma_f16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+            mma_f16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+            mma_commit(empty + stage);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          mma_commit(tmem_full + acc);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue: thread <-> row =====================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const unsigned row = (unsigned)tile * 128u + (unsigned)r;
+      const bool valid = row < n_pairs;
+      const int point = valid ? __ldg(p.rec_point + row) : 0;
+      const float sc = (kAccum && valid) ? __ldg(p.scale + row) : 0.f;
+      float ss = 0.f;
+      for (int c = 0; c < n_chunks; ++c) {
+        mbar_wait(tmem_full + acc, acc_phase);
+        fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+#pragma unroll 1
+        for (int cc = 0; cc < 8; ++cc) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + (uint32_t)(cc * 32), v);
+          tmem_ld_wait();
+          if (kAccum) {
+            // thread = row out of TMEM, but a warp-wide red of one row segment per thread would touch 32 half-used sectors:
+            // the 32 x 32 block goes through shared memory (row stride 36 floats) and comes back with 8 lanes per row,
+            // so one red instruction adds 4 rows x 128 contiguous bytes (16 full sectors)
+            float* tb = s_trans + (warp - kEpiWarp0) * (32 * 36);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(tb + lane * 36 + i) = make_float4(__uint_as_float(v[i]) * sc, __uint_as_float(v[i + 1]) * sc,
+                                                                          __uint_as_float(v[i + 2]) * sc, __uint_as_float(v[i + 3]) * sc);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + (lane >> 3);
+              const int pt = __shfl_sync(0xffffffffu, valid ? point : -1, rr);
+              const float4 q = *reinterpret_cast<const float4*>(tb + rr * 36 + (lane & 7) * 4);
+              if (pt >= 0) red_add_v4(p.out + (int64_t)pt * p.dim + c * 256 + cc * 32 + (lane & 7) * 4, q.x, q.y, q.z, q.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ss = fmaf(__uint_as_float(v[i]), __uint_as_float(v[i]), ss);
+          }
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (!kAccum && valid) p.norm2[row] = ss;
+    }
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    __syncwarp();
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// thread per sorted pair: similarity weight and the scale the ACCUM pass applies (weight / |f| under norm_feat, weight
+// otherwise; weight = 1 without similarity); also writes similarity_mask. Same fp64 chain as finish_weight (table of
+// (patch cell . query) dots interpolated with the fp64 bicubic weights, pos - max|mean(neg), one division by |f|, clip),
+// organised per thread: neighbouring pairs of the sorted order share their footprint, so the 16 x Q table loads of a warp
+// are broadcasts.
+__global__ void __launch_bounds__(kThreads) pair_weight_kernel(PixParams p, Footprints fp, int n_scenes, const int* __restrict__ rec_point,
+                                                               const uint32_t* __restrict__ rec_pix, const int* __restrict__ rec_key,
+                                                               const unsigned* __restrict__ n_pairs_dev, const float* __restrict__ norm2,
+                                                               float* __restrict__ scale) {
+  const unsigned n_pairs = *n_pairs_dev;
+  const int64_t hw = (int64_t)p.height * p.width;
+  for (unsigned pair = blockIdx.x * kThreads + threadIdx.x; pair < n_pairs; pair += gridDim.x * kThreads) {
+    const int key = __ldg(rec_key + pair);
+    const int v_glob = key / fp.per_view();
+    const uint32_t pp = __ldg(rec_pix + pair);
+    const int pu = (int)(pp & 0xffffu), pv = (int)(pp >> 16);
+    const float nrm = p.norm_feat ? sqrtf(__ldg(norm2 + pair)) : 1.f;
+    float weight = 1.f;
+    if (p.sim_kernel != DC_SIM_NONE) {
+      int lo = 0, hi = n_scenes;  // scene of the view: last s with view_off[s] <= v_glob
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (p.view_off[mid] <= v_glob) lo = mid; else hi = mid;
+      }
+      const int scene = lo;
+      const int n_q = (int)(p.query_off[scene + 1] - p.query_off[scene]);
+      const int id = seg_at(p.seg, p.seg_dtype, (int64_t)v_glob * hw + (int64_t)pv * p.width + pu);
+      weight = 0.f;  // pixels whose id has no query keep metric 0 (quirk q13)
+      if (id >= 0 && id < n_q) {
+        double wy64[4], wx64[4];
+        const int iy0 = cubic_weights64(pv, p.ph, p.height, wy64), ix0 = cubic_weights64(pu, p.pw, p.width, wx64);
+        const double* dots_view = p.dots + (int64_t)v_glob * p.ph * p.pw * p.q_stride;
+        const double* cell[16];
+#pragma unroll
+        for (int ty = 0; ty < 4; ++ty)
+#pragma unroll
+          for (int tx = 0; tx < 4; ++tx) {
+            const int cy = min(max(iy0 - 1 + ty, 0), p.ph - 1), cx = min(max(ix0 - 1 + tx, 0), p.pw - 1);
+            cell[ty * 4 + tx] = dots_view + ((int64_t)cy * p.pw + cx) * p.q_stride;
+          }
+        double pos = 0.0, red = (p.sim_kernel == DC_SIM_MAX) ? -INFINITY : 0.0;
+        bool nan_seen = false;
+        for (int o = 0; o < n_q; ++o) {
+          // the association of interp_dot: along x inside each row of taps, then along y
+          double mine = 0.0;
+#pragma unroll
+          for (int ty = 0; ty < 4; ++ty) {
+            double r = __ldg(cell[ty * 4] + o) * wx64[0];
+            r = fma(__ldg(cell[ty * 4 + 1] + o), wx64[1], r);
+            r = fma(__ldg(cell[ty * 4 + 2] + o), wx64[2], r);
+            r = fma(__ldg(cell[ty * 4 + 3] + o), wx64[3], r);
+            mine = fma(r, wy64[ty], mine);
+          }
+          if (o == id) pos = mine;
+          else {
+            nan_seen |= (mine != mine);
+            if (p.sim_kernel == DC_SIM_MAX) red = fmax(red, mine); else red += mine;
+          }
+        }
+        if (p.sim_kernel == DC_SIM_MEAN) red = red / (double)(n_q - 1);
+        if (nan_seen) red = __longlong_as_double(0x7ff8000000000000ll);
+        double w = pos - red;
+        if (p.norm_feat) w = w / (double)nrm;  // nrm = 0 (an all-zero feature): 0 / 0 = NaN like the reference's f / |f|
+        weight = (float)w;
+        if (weight == weight) weight = fmaxf(weight, 1e-6f);
+      }
+      if (p.out_weight) {
+        const int64_t p0 = p.point_off[scene], n_pts = p.point_off[scene + 1] - p0;
+        const int v_local = (int)(v_glob - p.view_off[scene]);
+        p.out_weight[p.mask_off[scene] + (int64_t)v_local * n_pts + (__ldg(rec_point + pair) - p0)] = weight;
+      }
+    }
+    scale[pair] = p.norm_feat ? weight / nrm : weight;  // (f / |f|) * weight; 0 / 0 = NaN like the reference
+  }
+}
+
+struct Workspace {
+  size_t dots, pix, counts, sums, total, rec_point, rec_pix, rec_key, arec, norm2, scale, plane_hi, plane_lo, bytes;
+  int64_t n_keys, n_scan_blocks;
+};
+Workspace layout(int64_t total_views, int64_t mask_elems, int ph, int pw, int dim, int max_q) {
+  Workspace w{};
+  size_t off = 0;
+  auto take = [&](size_t b) { const size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
+  const int64_t pairs = mask_elems > 0 ? mask_elems : 1;
+  w.n_keys = total_views * (ph + 1) * (pw + 1);
+  w.n_scan_blocks = (w.n_keys + kScanBlock - 1) / kScanBlock;
+  w.dots = take(max_q > 0 ? (size_t)total_views * ph * pw * query_stride_(max_q) * sizeof(double) : 0);
+  w.pix = take((size_t)pairs * 4);
+  w.counts = take((size_t)(w.n_keys > 0 ? w.n_keys : 1) * 4);
+  w.sums = take((size_t)(w.n_scan_blocks > 0 ? w.n_scan_blocks : 1) * 4);
+  w.total = take(256);
+  w.rec_point = take((size_t)pairs * 4);
+  w.rec_pix = take((size_t)pairs * 4);
+  w.rec_key = take((size_t)pairs * 4);
+  w.arec = take((size_t)pairs * 64);
+  w.norm2 = take((size_t)pairs * 4);
+  w.scale = take((size_t)pairs * 4);
+  w.plane_hi = take((size_t)total_views * ph * pw * dim * 2);
+  w.plane_lo = take((size_t)total_views * ph * pw * dim * 2);
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace mma
+
 unsigned blocks_for(int64_t max_points, int n_scenes) {
   int64_t want = dc::ceil_div<int64_t>(max_points, kWarps);
   int64_t cap = dc::ceil_div<int64_t>((int64_t)dc::sm_count() * 16, n_scenes);
@@ -735,6 +1327,94 @@ int dc_pixel_fuse(const double* points, const int64_t* point_off, const int64_t*
     }
   }
   DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+size_t dc_pixel_fuse_mma_workspace(int64_t total_views, int64_t mask_elems, int patch_h, int patch_w, int dim,
+                                   int max_queries_per_scene) {
+  if (total_views <= 0 || patch_h <= 0 || patch_w <= 0 || dim <= 0) return 0;
+  return mma::layout(total_views, mask_elems, patch_h, patch_w, dim, max_queries_per_scene).bytes;
+}
+
+int dc_pixel_fuse_mma(const double* points, const int64_t* point_off, const int64_t* view_off, const double* inv_poses,
+                      const double* intrinsics, const int64_t* mask_off, const uint8_t* visible, const void* seg, int seg_dtype,
+                      const float* patch_feats, int patch_h, int patch_w, int dim, const float* queries,
+                      const int64_t* query_off, int sim_kernel, int norm_feat, int n_scenes, int64_t max_points_per_scene,
+                      int max_views_per_scene, int height, int width, float* out_sum, float* out_weight, int normalize,
+                      int64_t total_views, int64_t total_points, int64_t mask_elems, int max_queries_per_scene,
+                      void* workspace, size_t workspace_bytes, dc_stream_t stream) {
+  DC_CHECK_ARG(points && point_off && view_off && inv_poses && intrinsics && mask_off && visible && patch_feats && out_sum && workspace,
+               "dc_pixel_fuse_mma: null pointer argument");
+  DC_CHECK_ARG(sim_kernel >= DC_SIM_NONE && sim_kernel <= DC_SIM_MEAN, "dc_pixel_fuse_mma: Please set method in [mean, max]");
+  DC_CHECK_ARG(sim_kernel == DC_SIM_NONE || (queries && query_off && seg && out_weight),
+               "dc_pixel_fuse_mma: similarity needs queries, seg and out_weight");
+  DC_CHECK_ARG(dim == 512 || dim == 768 || dim == 1024, "dc_pixel_fuse_mma: dim must be 512, 768 or 1024 (got %d)", dim);
+  DC_CHECK_ARG(patch_h > 0 && patch_w > 0 && height > 0 && width > 0 && height < 65536 && width < 65536, "dc_pixel_fuse_mma: bad sizes");
+  DC_CHECK_ARG((((uintptr_t)patch_feats | (uintptr_t)out_sum | (uintptr_t)workspace) & 255) == 0 || (((uintptr_t)workspace & 255) == 0 &&
+               (((uintptr_t)patch_feats | (uintptr_t)out_sum) & 15) == 0), "dc_pixel_fuse_mma: buffers must be 16-byte (workspace 256-byte) aligned");
+  if (n_scenes <= 0 || max_points_per_scene <= 0 || total_points <= 0) return DC_OK;
+  DC_CHECK_ARG(n_scenes <= 65535, "dc_pixel_fuse_mma: at most 65535 scenes per call");
+  DC_CHECK_ARG(total_points < (1ll << 31) && mask_elems < (1ll << 31), "dc_pixel_fuse_mma: too many points / pairs for one call");
+  DC_CHECK_ARG(total_views * (int64_t)(patch_h + 1) * (patch_w + 1) < (1ll << 31), "dc_pixel_fuse_mma: too many views for one call");
+  const mma::Workspace w = mma::layout(total_views, mask_elems, patch_h, patch_w, dim, sim_kernel != DC_SIM_NONE ? max_queries_per_scene : 0);
+  if (workspace_bytes < w.bytes) return dc::fail(DC_ERR_WORKSPACE, "dc_pixel_fuse_mma: workspace %zu < %zu", workspace_bytes, w.bytes);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  cudaStream_t st = dc::as_stream(stream);
+  PixParams p{points, point_off, view_off, inv_poses, intrinsics, mask_off, visible, seg, seg_dtype, patch_feats, patch_h,
+              patch_w, dim, queries, query_off, sim_kernel, norm_feat, height, width, nullptr, out_sum, out_weight, nullptr, 0, normalize};
+  const mma::Footprints fp{patch_h, patch_w, height, width};
+  unsigned* counts = reinterpret_cast<unsigned*>(ws + w.counts);
+  unsigned* sums = reinterpret_cast<unsigned*>(ws + w.sums);
+  unsigned* total = reinterpret_cast<unsigned*>(ws + w.total);
+  uint32_t* pix = reinterpret_cast<uint32_t*>(ws + w.pix);
+  int* rec_point = reinterpret_cast<int*>(ws + w.rec_point);
+  uint32_t* rec_pix = reinterpret_cast<uint32_t*>(ws + w.rec_pix);
+  int* rec_key = reinterpret_cast<int*>(ws + w.rec_key);
+  __half* arec = reinterpret_cast<__half*>(ws + w.arec);
+  float* norm2 = reinterpret_cast<float*>(ws + w.norm2);
+  float* scale = reinterpret_cast<float*>(ws + w.scale);
+  __half* plane_hi = reinterpret_cast<__half*>(ws + w.plane_hi);
+  __half* plane_lo = reinterpret_cast<__half*>(ws + w.plane_lo);
+  DC_CUDA(cudaMemsetAsync(counts, 0, (size_t)w.n_keys * 4, st));
+  DC_CUDA(cudaMemsetAsync(out_sum, 0, (size_t)total_points * dim * sizeof(float), st));
+  if (out_weight) DC_CUDA(cudaMemsetAsync(out_weight, 0, (size_t)mask_elems * sizeof(float), st));
+  if (sim_kernel != DC_SIM_NONE) {
+    p.dots = reinterpret_cast<double*>(ws + w.dots);
+    p.q_stride = query_stride(max_queries_per_scene);
+    if (total_views > 0 && max_queries_per_scene > 0) {
+      const int64_t rows = (int64_t)max_views_per_scene * patch_h * patch_w;
+      dim3 dgrid(blocks_for(rows, n_scenes), (unsigned)n_scenes);
+      patch_query_dots_kernel<<<dgrid, kThreads, 0, st>>>(p);
+      DC_LAUNCH_CHECK();
+    }
+  }
+  // fp16 hi / lo planes of the patch maps (the B operands)
+  int rc = dc_row_normalize(const_cast<float*>(patch_feats), DC_F32, total_views * patch_h * patch_w, dim, 0, plane_hi, plane_lo, stream);
+  if (rc) return rc;
+  // pairs sorted by (view, footprint)
+  int64_t chunks = dc::ceil_div<int64_t>(max_points_per_scene, kThreads);
+  const int64_t cap = dc::ceil_div<int64_t>((int64_t)dc::sm_count() * 16, n_scenes);
+  if (chunks > cap) chunks = cap;
+  dim3 pgrid((unsigned)(chunks < 1 ? 1 : chunks), (unsigned)n_scenes);
+  mma::pair_count_kernel<<<pgrid, kThreads, 0, st>>>(p, fp, pix, counts);
+  mma::scan_sums_kernel<<<(unsigned)w.n_scan_blocks, mma::kScanBlock, 0, st>>>(counts, w.n_keys, sums);
+  mma::scan_bases_kernel<<<1, mma::kScanBlock, 0, st>>>(sums, w.n_scan_blocks, total);
+  mma::scan_apply_kernel<<<(unsigned)w.n_scan_blocks, mma::kScanBlock, 0, st>>>(counts, w.n_keys, sums);
+  mma::pair_scatter_kernel<<<pgrid, kThreads, 0, st>>>(p, fp, pix, counts, rec_point, rec_pix, rec_key, arec);
+  DC_LAUNCH_CHECK();
+  mma::MmaParams mp{rec_point, rec_key, arec, plane_hi, plane_lo, total, patch_h, patch_w, dim, fp.per_view(), norm2, scale, out_sum};
+  DC_CUDA(cudaFuncSetAttribute(mma::pixel_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mma::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(mma::pixel_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mma::kSmemBytes));
+  const int64_t max_tiles = dc::ceil_div<int64_t>(mask_elems, 128);
+  const unsigned mgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(max_tiles, dc::sm_count()));
+  if (norm_feat) mma::pixel_mma_kernel<false><<<mgrid, mma::kThreadsMma, mma::kSmemBytes, st>>>(mp);
+  const unsigned wgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(dc::ceil_div<int64_t>(mask_elems, kThreads), (int64_t)dc::sm_count() * 16));
+  mma::pair_weight_kernel<<<wgrid, kThreads, 0, st>>>(p, fp, n_scenes, rec_point, rec_pix, rec_key, total, norm2, scale);
+  mma::pixel_mma_kernel<true><<<mgrid, mma::kThreadsMma, mma::kSmemBytes, st>>>(mp);
+  DC_LAUNCH_CHECK();
+  if (normalize)
+    return dc_pixel_normalize(out_sum, point_off, view_off, mask_off, visible, sim_kernel != DC_SIM_NONE ? out_weight : nullptr, n_scenes,
+                              max_points_per_scene, dim, stream);
   return DC_OK;
 }
 

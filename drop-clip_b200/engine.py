@@ -690,8 +690,12 @@ class FusionEngine:
         similarity weights [mask layout] f32 | None). `b.feats` is the (TV, ph, pw, C) patch stack.
         `normalize`: return the final features of fuse_points (:266-268) instead of the sums (fused division)."""
         tv, ph, pw, dim = b.feats.shape
-        sums = torch.empty((b.total_points, dim), dtype=torch.float32, device=b.device)
         kern = SIM_KERNELS[sim_kernel]
+        use_mma = (dim in (512, 768, 1024) and b.total_points > 0 and os.environ.get("DC_PIXEL_PATH", "mma") != "simt"
+                   and b.feats.dtype == torch.float32)
+        if use_mma:
+            return self._pixel_fuse_mma(b, mask_u8, kern, norm_feat, normalize)
+        sums = torch.empty((b.total_points, dim), dtype=torch.float32, device=b.device)
         weight = torch.empty(int(b.off_host["mask"][-1]), dtype=torch.float32, device=b.device) \
             if kern != _lib.DC_SIM_NONE else None
         segs = b.segs if kern != _lib.DC_SIM_NONE else None
@@ -707,6 +711,28 @@ class FusionEngine:
             max(b.n_views, default=0), b.height, b.width, ptr(perm), ptr(sums), ptr(weight), int(bool(normalize)), int(tv), max_q, ptr(ws), ws_bytes,
             current_stream()))
         self.launches += 3 if kern != _lib.DC_SIM_NONE else 1
+        return sums, weight
+
+    def _pixel_fuse_mma(self, b: SceneBatch, mask_u8, kern: int, norm_feat: bool, normalize: bool):
+        """The tcgen05 form of pixel_fuse (dc_pixel_fuse_mma): pairs sorted by bicubic footprint, 128-pair MMA tiles."""
+        tv, ph, pw, dim = b.feats.shape
+        mask_elems = int(b.off_host["mask"][-1])
+        sums = torch.empty((b.total_points, dim), dtype=torch.float32, device=b.device)
+        has_sim = kern != _lib.DC_SIM_NONE
+        weight = torch.empty(max(mask_elems, 1), dtype=torch.float32, device=b.device)[:mask_elems] if has_sim else None
+        max_q = max(b.n_queries, default=0) if has_sim else 0
+        ws_bytes = self.lib.dc_pixel_fuse_mma_workspace(int(tv), mask_elems, int(ph), int(pw), int(dim), max_q)
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=b.device)
+        shift = (-ws.data_ptr()) % 256
+        segs = b.segs if has_sim else None
+        check(self.lib.dc_pixel_fuse_mma(
+            ptr(b.points), ptr(b.off["point"]), ptr(b.off["view"]), ptr(b.inv_poses), ptr(b.intrinsics), ptr(b.off["mask"]),
+            ptr(mask_u8), ptr(segs), _lib.torch_dtype_code(segs.dtype) if segs is not None else _lib.DC_I64, ptr(b.feats),
+            int(ph), int(pw), int(dim), ptr(b.queries) if has_sim else None, ptr(b.off["query"]) if has_sim else None, kern,
+            int(bool(norm_feat)), b.n_scenes, max(b.n_points, default=0), max(b.n_views, default=0), b.height, b.width,
+            ptr(sums), ptr(weight), int(bool(normalize)), int(tv), b.total_points, mask_elems, max_q,
+            ctypes.c_void_p(ws.data_ptr() + shift), ws_bytes, current_stream()))
+        self.launches += 12 + int(has_sim) + int(bool(norm_feat)) + int(bool(normalize))
         return sums, weight
 
     def spatial_sort(self, b: SceneBatch):

@@ -259,6 +259,24 @@ DC_API int dc_pixel_fuse(const double* points, const int64_t* point_off, const i
                   int height, int width, const int64_t* perm, float* out_sum, float* out_weight, int normalize,
                   int64_t total_views, int max_queries_per_scene, void* workspace, size_t workspace_bytes,
                   dc_stream_t stream);
+/* The same computation on the tensor cores (dim 512 / 768 / 1024): the visible (point, view) pairs are counting-sorted by
+ * (view, bicubic footprint), every 128 sorted pairs form a tcgen05 tile D[128 x dim] = sum_segments A_g[128 x 16] . B_g[16 x dim]
+ * (A = the pairs' 16 tap weights, B = the footprint's 16 taps, fp16 hi/lo planes for fp32 accuracy), a first pass yields
+ * |f| per pair (norm_feat), the similarity weights follow from the (patch cell . query) table in fp64, and the second pass
+ * scales each row in the TMEM epilogue and adds it to its point's row (red.global.add.v4.f32: the order of the additions
+ * over a point's views is not fixed; results differ from the view-ordered sum by fp32 rounding only).
+ * Arguments as dc_pixel_fuse plus total_points and mask_elems (= mask_off[n_scenes]); out_weight is required when
+ * sim_kernel != NONE; workspace 256-byte aligned, dc_pixel_fuse_mma_workspace() bytes. */
+DC_API size_t dc_pixel_fuse_mma_workspace(int64_t total_views, int64_t mask_elems, int patch_h, int patch_w, int dim,
+                                   int max_queries_per_scene);
+DC_API int dc_pixel_fuse_mma(const double* points, const int64_t* point_off, const int64_t* view_off,
+                      const double* inv_poses, const double* intrinsics, const int64_t* mask_off,
+                      const uint8_t* visible, const void* seg, int seg_dtype, const float* patch_feats, int patch_h,
+                      int patch_w, int dim, const float* queries, const int64_t* query_off, int sim_kernel,
+                      int norm_feat, int n_scenes, int64_t max_points_per_scene, int max_views_per_scene,
+                      int height, int width, float* out_sum, float* out_weight, int normalize, int64_t total_views,
+                      int64_t total_points, int64_t mask_elems, int max_queries_per_scene, void* workspace,
+                      size_t workspace_bytes, dc_stream_t stream);
 /* workspace of dc_pixel_fuse when sim_kernel != NONE: the per-view (patch cell x query) dot table (0 bytes otherwise) */
 DC_API size_t dc_pixel_fuse_workspace(int64_t total_views, int patch_h, int patch_w, int max_queries_per_scene);
 /* generate_view_clip (data/dataset_blender.py:132-171): out[v, i, :] = bicubic(patch_feats[v])[clip(pixel of point i in view v)].
