@@ -691,8 +691,26 @@ def other_configs(dev, eng):
     pairs = int(mask.sum().item())
     out["pixel_level_fusion"] = {"workload": "configs[3]: 1 scene, V=8, N=100k, C=768, Q=21, 24x32 patch maps, sim max, norm_feat",
                                  "ms_per_scene": ms, "visible_point_views": pairs,
-                                 "tap_tflops": 2.0 * 16 * 768 * pairs / (ms * 1e-3) / 1e12}
+                                 "tap_tflops": 2.0 * 16 * 768 * pairs / (ms * 1e-3) / 1e12,
+                                 "kernel": "dc_pixel_fuse_mma (tcgen05: pairs sorted by bicubic footprint, 128-pair tiles)"}
     del b, mask, patches, sc, sc_obj
+    try:  # the same at the full view set
+        sc = make_scene(1234, n_views=73, n_points=100_000, n_objects=21, device=str(dev), as_torch=True, pixel_features=True,
+                        feature_dtype=torch.float32)
+        patches = torch.stack(sc["mv_features"]).contiguous()
+        sc_obj = dict(sc)
+        sc_obj["mv_features"] = [torch.zeros((1, 768), device=dev, dtype=torch.float16) for _ in range(73)]
+        b = batch_from_device([sc_obj], dev)
+        b.feats = patches
+        mask, _, _ = eng.visibility(b, 0.05, torch.uint8)
+        ms73 = median_ms(lambda: eng.pixel_fuse(b, mask, "max", True, normalize=True))
+        pairs73 = int(mask.sum().item())
+        out["pixel_level_fusion_V73"] = {"workload": "1 scene, V=73, N=100k, C=768, Q=21, sim max, norm_feat", "ms_per_scene": ms73,
+                                         "visible_point_views": pairs73, "tap_tflops": 2.0 * 16 * 768 * pairs73 / (ms73 * 1e-3) / 1e12}
+        del b, mask, patches, sc, sc_obj
+    except Exception as exc:
+        out["pixel_level_fusion_V73"] = {"error": repr(exc)}
+    torch.cuda.empty_cache()
 
     from dropclip_b200 import _lib as lib_mod
     n, p, c = 200_000, 256, 768

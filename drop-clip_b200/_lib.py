@@ -50,7 +50,7 @@ SIGNATURES = {
                               c_int, c_int, c_int, P, P, P, c_int, c_int64, c_int, P, c_size_t, P]),
     "dc_pixel_fuse_mma_workspace": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "dc_pixel_fuse_mma": (c_int, [P, P, P, P, P, P, P, P, c_int, P, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int64,
-                                  c_int, c_int, c_int, P, P, c_int, c_int64, c_int64, c_int64, c_int, P, c_size_t, P]),
+                                  c_int, c_int, c_int, P, P, P, c_int, c_int64, c_int64, c_int64, c_int, P, c_size_t, P]),
     "dc_pixel_fuse_workspace": (c_size_t, [c_int64, c_int, c_int, c_int]),
     "dc_spatial_sort_workspace": (c_size_t, [c_int]),
     "dc_spatial_sort": (c_int, [P, P, c_int, c_int64, c_int64, P, P, P, c_size_t, P]),

@@ -13,6 +13,7 @@
 // Bicubic weights follow ATen's upsample_bicubic2d (align_corners=False, A=-0.75, source index
 // scale*(dst+0.5)-0.5 un-clamped, taps clamped to the border).
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -687,7 +688,21 @@ constexpr int kSmemBytes = kStages * kStageBytes + 128 /*align*/ + 512 /*barrier
 
 struct Footprints {
   int ph, pw, height, width;
+  // Sort key = (region, global view, footprint). A region is a contiguous range of the scene's Morton order (rank from
+  // dc_spatial_sort): all tiles of region 0 (every view) come first, then region 1, ... so that the output rows the
+  // accumulate pass adds to at any time (one region: N / n_regions rows) stay resident in L2; being spatially compact, a
+  // region keeps the pairs-per-footprint density of the whole scene. rank == nullptr: one region.
+  int n_regions;
+  int64_t total_views;
+  const int64_t* rank;
   __host__ __device__ int per_view() const { return (ph + 1) * (pw + 1); }
+  __device__ int region_of(int64_t global_point, int64_t n_pts) const {
+    if (!rank || n_regions <= 1) return 0;
+    const int r = (int)((rank[global_point] * n_regions) / n_pts);
+    return r < n_regions ? r : n_regions - 1;
+  }
+  __device__ int key_of(int region, int64_t v_glob, int fp) const { return (int)((region * total_views + v_glob) * per_view() + fp); }
+  __device__ int view_of_key(int key) const { return (int)((key / per_view()) % total_views); }
 };
 
 // first source cell of the bicubic footprint of destination pixel `dst` (ATen: floor(scale * (dst + 0.5) - 0.5)), in [-1, in - 1]
@@ -733,6 +748,7 @@ __global__ void __launch_bounds__(kThreads) pair_count_kernel(PixParams p, Footp
   for (int e = 0; e < 9; ++e) K[e] = __ldg(p.intrinsics + (int64_t)scene * 9 + e);
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_pts; i += (int64_t)gridDim.x * kThreads) {
     const double x = __ldg(p.points + 3 * (p0 + i)), y = __ldg(p.points + 3 * (p0 + i) + 1), z = __ldg(p.points + 3 * (p0 + i) + 2);
+    const int region = fp.region_of(p0 + i, n_pts);
     for (int v = 0; v < n_views; ++v) {
       if (!vis[(int64_t)v * n_pts + i]) continue;
       double m[12];
@@ -741,7 +757,7 @@ __global__ void __launch_bounds__(kThreads) pair_count_kernel(PixParams p, Footp
       int pu, pv;
       project_pixel(m, K, x, y, z, pu, pv);
       px[(int64_t)v * n_pts + i] = (uint32_t)pu | ((uint32_t)pv << 16);
-      atomicAdd(counts + (v0 + v) * fp.per_view() + footprint_of(fp, pu, pv), 1u);
+      atomicAdd(counts + fp.key_of(region, v0 + v, footprint_of(fp, pu, pv)), 1u);
     }
   }
 }
@@ -837,11 +853,12 @@ __global__ void __launch_bounds__(kThreads) pair_scatter_kernel(PixParams p, Foo
   const uint8_t* vis = p.visible + p.mask_off[scene];
   const uint32_t* px = pix + p.mask_off[scene];
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_pts; i += (int64_t)gridDim.x * kThreads) {
+    const int region = fp.region_of(p0 + i, n_pts);
     for (int v = 0; v < n_views; ++v) {
       if (!vis[(int64_t)v * n_pts + i]) continue;
       const uint32_t pp = px[(int64_t)v * n_pts + i];
       const int pu = (int)(pp & 0xffffu), pv = (int)(pp >> 16);
-      const int key = (int)((v0 + v) * fp.per_view() + footprint_of(fp, pu, pv));
+      const int key = fp.key_of(region, v0 + v, footprint_of(fp, pu, pv));
       const unsigned pos = atomicAdd(cursor + key, 1u);
       rec_point[pos] = (int)(p0 + i);
       rec_pix[pos] = pp;
@@ -898,6 +915,7 @@ struct MmaParams {
   const __half* plane_lo;
   const unsigned* n_pairs;  // device scalar
   int ph, pw, dim, nfp;     // nfp = footprints per view
+  int total_views;          // key = (region * total_views + view) * nfp + footprint
   float* norm2;             // [pairs]  (pass NORM)
   const float* scale;       // [pairs]  (pass ACCUM)
   float* out;               // [total_points][dim]
@@ -1007,7 +1025,8 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
             *reinterpret_cast<int4*>(arow + kABytes) = mine ? a_lo0 : z;
             *reinterpret_cast<int4*>(arow + kABytes + 2048) = mine ? a_lo1 : z;
             // B: 16 taps x 256 channels of both planes, 16 bytes per copy
-            const int v_glob = seg_key / p.nfp, f = seg_key - v_glob * p.nfp;
+            const int vk = seg_key / p.nfp, f = seg_key - vk * p.nfp;
+            const int v_glob = vk % p.total_views;
             const int iy0 = f / (p.pw + 1) - 1, ix0 = f - (f / (p.pw + 1)) * (p.pw + 1) - 1;
             uint8_t* bh = st + 2 * kABytes;
             uint8_t* bl = bh + kBBytes;
@@ -1149,7 +1168,7 @@ __global__ void __launch_bounds__(kThreads) pair_weight_kernel(PixParams p, Foot
   const int64_t hw = (int64_t)p.height * p.width;
   for (unsigned pair = blockIdx.x * kThreads + threadIdx.x; pair < n_pairs; pair += gridDim.x * kThreads) {
     const int key = __ldg(rec_key + pair);
-    const int v_glob = key / fp.per_view();
+    const int v_glob = fp.view_of_key(key);
     const uint32_t pp = __ldg(rec_pix + pair);
     const int pu = (int)(pp & 0xffffu), pv = (int)(pp >> 16);
     const float nrm = p.norm_feat ? sqrtf(__ldg(norm2 + pair)) : 1.f;
@@ -1216,12 +1235,13 @@ struct Workspace {
   size_t dots, pix, counts, sums, total, rec_point, rec_pix, rec_key, arec, norm2, scale, plane_hi, plane_lo, bytes;
   int64_t n_keys, n_scan_blocks;
 };
+constexpr int kMaxRegions = 32;
 Workspace layout(int64_t total_views, int64_t mask_elems, int ph, int pw, int dim, int max_q) {
   Workspace w{};
   size_t off = 0;
   auto take = [&](size_t b) { const size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
   const int64_t pairs = mask_elems > 0 ? mask_elems : 1;
-  w.n_keys = total_views * (ph + 1) * (pw + 1);
+  w.n_keys = (int64_t)kMaxRegions * total_views * (ph + 1) * (pw + 1);  // sized for the most regions; a call scans what it uses
   w.n_scan_blocks = (w.n_keys + kScanBlock - 1) / kScanBlock;
   w.dots = take(max_q > 0 ? (size_t)total_views * ph * pw * query_stride_(max_q) * sizeof(double) : 0);
   w.pix = take((size_t)pairs * 4);
@@ -1340,8 +1360,8 @@ int dc_pixel_fuse_mma(const double* points, const int64_t* point_off, const int6
                       const double* intrinsics, const int64_t* mask_off, const uint8_t* visible, const void* seg, int seg_dtype,
                       const float* patch_feats, int patch_h, int patch_w, int dim, const float* queries,
                       const int64_t* query_off, int sim_kernel, int norm_feat, int n_scenes, int64_t max_points_per_scene,
-                      int max_views_per_scene, int height, int width, float* out_sum, float* out_weight, int normalize,
-                      int64_t total_views, int64_t total_points, int64_t mask_elems, int max_queries_per_scene,
+                      int max_views_per_scene, int height, int width, const int64_t* rank, float* out_sum, float* out_weight,
+                      int normalize, int64_t total_views, int64_t total_points, int64_t mask_elems, int max_queries_per_scene,
                       void* workspace, size_t workspace_bytes, dc_stream_t stream) {
   DC_CHECK_ARG(points && point_off && view_off && inv_poses && intrinsics && mask_off && visible && patch_feats && out_sum && workspace,
                "dc_pixel_fuse_mma: null pointer argument");
@@ -1355,14 +1375,24 @@ int dc_pixel_fuse_mma(const double* points, const int64_t* point_off, const int6
   if (n_scenes <= 0 || max_points_per_scene <= 0 || total_points <= 0) return DC_OK;
   DC_CHECK_ARG(n_scenes <= 65535, "dc_pixel_fuse_mma: at most 65535 scenes per call");
   DC_CHECK_ARG(total_points < (1ll << 31) && mask_elems < (1ll << 31), "dc_pixel_fuse_mma: too many points / pairs for one call");
-  DC_CHECK_ARG(total_views * (int64_t)(patch_h + 1) * (patch_w + 1) < (1ll << 31), "dc_pixel_fuse_mma: too many views for one call");
-  const mma::Workspace w = mma::layout(total_views, mask_elems, patch_h, patch_w, dim, sim_kernel != DC_SIM_NONE ? max_queries_per_scene : 0);
+  // regions: the rows one region adds to should fit well inside the 126 MB L2 (~24 MB per region), while every scene keeps
+  // enough points per region for full tiles
+  int n_regions = 1;
+  if (rank && !getenv("DC_PIXEL_ONE_REGION")) {
+    const int64_t row_bytes = (int64_t)dim * 4;
+    const int64_t want = dc::ceil_div<int64_t>(max_points_per_scene * n_scenes * row_bytes, (int64_t)24 << 20);
+    n_regions = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, mma::kMaxRegions), max_points_per_scene / 2048));
+  }
+  DC_CHECK_ARG((int64_t)n_regions * total_views * (int64_t)(patch_h + 1) * (patch_w + 1) < (1ll << 31), "dc_pixel_fuse_mma: too many views for one call");
+  mma::Workspace w = mma::layout(total_views, mask_elems, patch_h, patch_w, dim, sim_kernel != DC_SIM_NONE ? max_queries_per_scene : 0);
   if (workspace_bytes < w.bytes) return dc::fail(DC_ERR_WORKSPACE, "dc_pixel_fuse_mma: workspace %zu < %zu", workspace_bytes, w.bytes);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   cudaStream_t st = dc::as_stream(stream);
   PixParams p{points, point_off, view_off, inv_poses, intrinsics, mask_off, visible, seg, seg_dtype, patch_feats, patch_h,
               patch_w, dim, queries, query_off, sim_kernel, norm_feat, height, width, nullptr, out_sum, out_weight, nullptr, 0, normalize};
-  const mma::Footprints fp{patch_h, patch_w, height, width};
+  const mma::Footprints fp{patch_h, patch_w, height, width, n_regions, total_views, rank};
+  w.n_keys = (int64_t)n_regions * total_views * fp.per_view();
+  w.n_scan_blocks = (w.n_keys + mma::kScanBlock - 1) / mma::kScanBlock;
   unsigned* counts = reinterpret_cast<unsigned*>(ws + w.counts);
   unsigned* sums = reinterpret_cast<unsigned*>(ws + w.sums);
   unsigned* total = reinterpret_cast<unsigned*>(ws + w.total);
@@ -1402,7 +1432,7 @@ int dc_pixel_fuse_mma(const double* points, const int64_t* point_off, const int6
   mma::scan_apply_kernel<<<(unsigned)w.n_scan_blocks, mma::kScanBlock, 0, st>>>(counts, w.n_keys, sums);
   mma::pair_scatter_kernel<<<pgrid, kThreads, 0, st>>>(p, fp, pix, counts, rec_point, rec_pix, rec_key, arec);
   DC_LAUNCH_CHECK();
-  mma::MmaParams mp{rec_point, rec_key, arec, plane_hi, plane_lo, total, patch_h, patch_w, dim, fp.per_view(), norm2, scale, out_sum};
+  mma::MmaParams mp{rec_point, rec_key, arec, plane_hi, plane_lo, total, patch_h, patch_w, dim, fp.per_view(), (int)total_views, norm2, scale, out_sum};
   DC_CUDA(cudaFuncSetAttribute(mma::pixel_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mma::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(mma::pixel_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mma::kSmemBytes));
   const int64_t max_tiles = dc::ceil_div<int64_t>(mask_elems, 128);

@@ -725,12 +725,14 @@ class FusionEngine:
         ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=b.device)
         shift = (-ws.data_ptr()) % 256
         segs = b.segs if has_sim else None
+        # Morton rank of the points: pairs are grouped by spatial region so that the rows being accumulated stay in L2
+        rank = self.spatial_sort(b)[1] if b.total_points * dim * 4 > (48 << 20) else None
         check(self.lib.dc_pixel_fuse_mma(
             ptr(b.points), ptr(b.off["point"]), ptr(b.off["view"]), ptr(b.inv_poses), ptr(b.intrinsics), ptr(b.off["mask"]),
             ptr(mask_u8), ptr(segs), _lib.torch_dtype_code(segs.dtype) if segs is not None else _lib.DC_I64, ptr(b.feats),
             int(ph), int(pw), int(dim), ptr(b.queries) if has_sim else None, ptr(b.off["query"]) if has_sim else None, kern,
             int(bool(norm_feat)), b.n_scenes, max(b.n_points, default=0), max(b.n_views, default=0), b.height, b.width,
-            ptr(sums), ptr(weight), int(bool(normalize)), int(tv), b.total_points, mask_elems, max_q,
+            ptr(rank), ptr(sums), ptr(weight), int(bool(normalize)), int(tv), b.total_points, mask_elems, max_q,
             ctypes.c_void_p(ws.data_ptr() + shift), ws_bytes, current_stream()))
         self.launches += 12 + int(has_sim) + int(bool(norm_feat)) + int(bool(normalize))
         return sums, weight

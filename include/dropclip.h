@@ -265,6 +265,8 @@ DC_API int dc_pixel_fuse(const double* points, const int64_t* point_off, const i
  * |f| per pair (norm_feat), the similarity weights follow from the (patch cell . query) table in fp64, and the second pass
  * scales each row in the TMEM epilogue and adds it to its point's row (red.global.add.v4.f32: the order of the additions
  * over a point's views is not fixed; results differ from the view-ordered sum by fp32 rounding only).
+ * `rank` [total_points] from dc_spatial_sort or NULL: with it the pairs are grouped by Morton-contiguous point regions first, so
+ * that the output rows being added to stay resident in L2 (without it the accumulate pass misses L2 on most additions).
  * Arguments as dc_pixel_fuse plus total_points and mask_elems (= mask_off[n_scenes]); out_weight is required when
  * sim_kernel != NONE; workspace 256-byte aligned, dc_pixel_fuse_mma_workspace() bytes. */
 DC_API size_t dc_pixel_fuse_mma_workspace(int64_t total_views, int64_t mask_elems, int patch_h, int patch_w, int dim,
@@ -274,9 +276,9 @@ DC_API int dc_pixel_fuse_mma(const double* points, const int64_t* point_off, con
                       const uint8_t* visible, const void* seg, int seg_dtype, const float* patch_feats, int patch_h,
                       int patch_w, int dim, const float* queries, const int64_t* query_off, int sim_kernel,
                       int norm_feat, int n_scenes, int64_t max_points_per_scene, int max_views_per_scene,
-                      int height, int width, float* out_sum, float* out_weight, int normalize, int64_t total_views,
-                      int64_t total_points, int64_t mask_elems, int max_queries_per_scene, void* workspace,
-                      size_t workspace_bytes, dc_stream_t stream);
+                      int height, int width, const int64_t* rank, float* out_sum, float* out_weight, int normalize,
+                      int64_t total_views, int64_t total_points, int64_t mask_elems, int max_queries_per_scene,
+                      void* workspace, size_t workspace_bytes, dc_stream_t stream);
 /* workspace of dc_pixel_fuse when sim_kernel != NONE: the per-view (patch cell x query) dot table (0 bytes otherwise) */
 DC_API size_t dc_pixel_fuse_workspace(int64_t total_views, int patch_h, int patch_w, int max_queries_per_scene);
 /* generate_view_clip (data/dataset_blender.py:132-171): out[v, i, :] = bicubic(patch_feats[v])[clip(pixel of point i in view v)].

@@ -856,10 +856,12 @@ def test_sorted_filter_randomised_differential_vs_literal_kernel(seed):
 # The golden pixel-level cases have 64-d features and therefore run the generic kernel; the CLIP widths (512 / 768 /
 # 1024) take the tile kernel (shared-memory accumulators, per-view dot table, fused division). Same reference
 # arithmetic through the oracle (itself pinned by the 64-d golden files in test_oracle_golden.py).
+@pytest.mark.parametrize("path", ["mma", "simt"])  # tcgen05 footprint-sorted path (default) / SIMT tile kernel
 @pytest.mark.parametrize("dim,n_objects,sim", [(768, 5, "max"), (512, 40, "mean"), (1024, 3, "max"), (768, 5, None)])
-def test_pixel_level_tile_kernel_vs_oracle(dim, n_objects, sim):
+def test_pixel_level_tile_kernel_vs_oracle(dim, n_objects, sim, path, monkeypatch):
     from dropclip_b200.scenes import small_scene
     from oracle import fusion_ref as fr
+    monkeypatch.setenv("DC_PIXEL_PATH", path)
     sc = small_scene(500 + dim + n_objects, n_views=4, n_points=1800, n_objects=n_objects, height=96, width=128, feat_dim=dim,
                      feature_dtype=torch.float32, pixel_features=True, patch_hw=(6, 8))
     us, nf = (1 if sim else 0), dim != 512
@@ -903,3 +905,39 @@ def test_wide_uint8_unpack_equals_byte_unpack_at_every_row_alignment():
     # device-resident layout (upper-bound buffers): same bytes in front, nothing written behind
     _, _, _, off_dev, wide_dev, _ = eng.compact_visibility(b, any_s, records, rank, torch.uint8, host_sizes=False)
     assert torch.equal(wide_dev[:narrow.numel()], narrow)
+
+
+def test_pixel_mma_path_equals_simt_path_on_a_ragged_batch(monkeypatch):
+    """dc_pixel_fuse_mma on a batch of scenes with different view / point / query counts (global view indices, per-scene
+    query tables, a scene nobody sees, ids without a query): sums, weights and normalised features against the SIMT tile
+    kernel (itself checked against the oracle above) at the 1e-3 bar, NaN patterns identical."""
+    from dropclip_b200.engine import FusionEngine, batch_from_device
+    from dropclip_b200.scenes import make_scene, scaled_intrinsic
+    eng = FusionEngine("cuda")
+    shapes = [(3000, 5, 6), (1200, 3, 40), (2500, 7, 4), (800, 2, 9)]
+    scenes = []
+    for i, (n, v, q) in enumerate(shapes):
+        sc = make_scene(4200 + i, n_views=v, n_points=n, n_objects=q, intrinsic=scaled_intrinsic(96, 128), device="cuda", as_torch=True,
+                        pixel_features=True, feature_dtype=torch.float32, patch_hw=(6, 8))
+        scenes.append(sc)
+    scenes[2]["points"] = scenes[2]["points"] + 1e4          # nobody sees this scene
+    scenes[0]["seg_masks"] = scenes[0]["seg_masks"].clone()
+    scenes[0]["seg_masks"][:, :20, :30] = 17                 # an id without a query: weight 0 (quirk q13)
+    patches = torch.cat([torch.stack(sc["mv_features"]) for sc in scenes]).contiguous()
+    objs = [dict(sc, mv_features=[torch.zeros((1, 768), device="cuda", dtype=torch.float16) for _ in sc["mv_features"]]) for sc in scenes]
+    b = batch_from_device(objs, "cuda")
+    b.feats = patches
+    mask, _, _ = eng.visibility(b, 0.05, torch.uint8)
+    for kern, nf, normalize in (("max", True, True), ("mean", False, True), (None, True, False), ("max", True, False)):
+        res = {}
+        for path in ("mma", "simt"):
+            monkeypatch.setenv("DC_PIXEL_PATH", path)
+            sums, w = eng.pixel_fuse(b, mask, kern, nf, normalize=normalize)
+            torch.cuda.synchronize()
+            res[path] = (sums.cpu().numpy(), None if w is None else w.cpu().numpy())
+        (sa, wa), (sb, wb) = res["mma"], res["simt"]
+        assert np.array_equal(np.isnan(sa), np.isnan(sb)), (kern, nf, normalize)
+        rel_close(np.nan_to_num(sa), np.nan_to_num(sb), what=f"mma vs simt sums {kern} {nf} {normalize}")
+        if kern:
+            assert np.array_equal(wa == 0, wb == 0)
+            np.testing.assert_allclose(wa, wb, rtol=1e-3, atol=1e-9)
