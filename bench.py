@@ -527,6 +527,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
         e2e = e2e_pipeline(args, dev, host, world, dist if world > 1 else None)
         e2e["reference_shaped_fuse"] = ref_shaped
+
         del host
 
     # ---- BASELINE configs 4 and 5 (supplementary; rank 0, N=1)
@@ -575,6 +576,13 @@ def e2e_pipeline(args, dev, host, world, dist):
     from dropclip_b200.scenes import make_scene
     rank = int(os.environ.get("RANK", "0"))
     n_slots, B = args.e2e_slots, args.e2e_batch
+    cores = None
+    if world > 1 and not os.environ.get("DC_BENCH_NO_PIN"):
+        # every rank keeps its pipeline threads (and the pinned slots it allocates from here on) on its own slice of the host
+        # cores - the cores NVML reports as local to its GPU when the box exposes that (shard.pin_rank_cores)
+        from dropclip_b200 import shard
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        cores = shard.pin_rank_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)), local)
     pipe = FusionPipeline(host[0].intrinsic, device=dev, batch_scenes=B, n_slots=n_slots, max_views=args.views,
                           max_points=max(s.points.shape[0] for s in host), max_queries=args.objects)
     slots, fill_s, fill_bytes = [], 0.0, 0
@@ -603,6 +611,20 @@ def e2e_pipeline(args, dev, host, world, dist):
         hprobe.copy_(probe, non_blocking=True)
     torch.cuda.synchronize()
     pcie_d2h = 4 * probe.numel() * 4 / (time.perf_counter() - t0) / 1e9
+    # the same copy with ALL ranks of the box copying at once: the host's memory system feeds every GPU's DMA engine, so
+    # this, not the solo rate, bounds a rank's H2D rate at N > 1
+    pcie_h2d_all = pcie_h2d
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(8):
+            probe.copy_(slots[0].t_depths, non_blocking=True)
+        torch.cuda.synchronize()
+        mine = torch.tensor([8 * probe.numel() * 4 / (time.perf_counter() - t0) / 1e9], device=dev)
+        dist.all_reduce(mine, op=dist.ReduceOp.MIN)
+        pcie_h2d_all = float(mine.item())
+        dist.barrier()
     del probe, hprobe
     done = [0]
     res_bytes = [0]
@@ -649,8 +671,11 @@ def e2e_pipeline(args, dev, host, world, dist):
             "h2d_bytes_per_step": int(h2d // n_scenes * B), "d2h_bytes_per_step": int(d2h // n_scenes * B),
             "h2d_gbs_per_gpu": h2d / dt / 1e9, "d2h_gbs_per_gpu": d2h / dt / 1e9,
             "bound": {"kind": "pcie_h2d", "pinned_h2d_gbs": pcie_h2d, "pinned_d2h_gbs": pcie_d2h,
-                      "frac_of_bound": (h2d / dt / 1e9) / pcie_h2d,
-                      "note": "plain pinned->device copy of one slot's depth block on this box, measured in this run"},
+                      "pinned_h2d_gbs_all_ranks_at_once": pcie_h2d_all,
+                      "frac_of_bound": (h2d / dt / 1e9) / pcie_h2d_all, "frac_of_solo_rate": (h2d / dt / 1e9) / pcie_h2d,
+                      "host_cores_per_rank": len(cores) if cores else host_cores(),
+                      "note": "plain pinned->device copies of one slot's depth block on this box, measured in this run: alone, "
+                              "and with every rank copying at the same time (slowest rank; the bound at N > 1)"},
             "host_fill": {"gbs": fill_bytes / fill_s / 1e9, "ms_per_scene": 1e3 * fill_s / n_slots,
                           "note": "PinnedSceneSlot.fill() from the reference's pageable numpy containers (int64 maps narrowed "
                                   "to uint8 on the way), outside the timed region: a loader writes the slot once"},

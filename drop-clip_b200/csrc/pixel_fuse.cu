@@ -756,6 +756,9 @@ __global__ void __launch_bounds__(kThreads) pair_count_kernel(PixParams p, Footp
       for (int e = 0; e < 12; ++e) m[e] = __ldg(p.inv_poses + (v0 + v) * 16 + e);
       int pu, pv;
       project_pixel(m, K, x, y, z, pu, pv);
+      // a pair the visibility kernels marked visible projects inside the image; a hand-made mask must not index outside
+      pu = min(max(pu, 0), p.width - 1);
+      pv = min(max(pv, 0), p.height - 1);
       px[(int64_t)v * n_pts + i] = (uint32_t)pu | ((uint32_t)pv << 16);
       atomicAdd(counts + fp.key_of(region, v0 + v, footprint_of(fp, pu, pv)), 1u);
     }

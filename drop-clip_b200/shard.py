@@ -323,9 +323,30 @@ def rank_scene_ids(scene_ids: Sequence[int], rank: int, world: int, split: str =
     raise ValueError("split must be 'strided' or 'reference'")
 
 
-def pin_rank_cores(rank_local: Optional[int] = None, world_local: Optional[int] = None) -> List[int]:
-    """Gives each rank of a node its own contiguous slice of the host cores (loader, staging and writer threads of
-    different ranks then never share a core or an L2). Returns the cores now allowed; no-op for one rank."""
+def _gpu_local_cores(device_index: int) -> List[int]:
+    """CPUs NVML reports as local to the GPU (its NUMA node / PCIe root), [] when unknown."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device_index
+        if visible:
+            parts = visible.split(",")
+            if device_index < len(parts) and parts[device_index].isdigit():
+                idx = int(parts[device_index])
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        n_cpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        return [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+    except Exception:
+        return []
+
+
+def pin_rank_cores(rank_local: Optional[int] = None, world_local: Optional[int] = None, device_index: Optional[int] = None) -> List[int]:
+    """Gives each rank of a node its own slice of the host cores, taken from the cores local to ITS GPU when NVML knows
+    them (pinned staging memory allocated afterwards then sits on the GPU's NUMA node, and the loader / staging / writer
+    threads of different ranks never share a core). Without NVML affinity information: contiguous slices of the allowed
+    cores by local rank. Returns the cores now allowed; no-op for one rank."""
     rank_local = int(os.environ.get("LOCAL_RANK", "0")) if rank_local is None else rank_local
     world_local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1) if world_local is None else world_local
     try:
@@ -334,8 +355,18 @@ def pin_rank_cores(rank_local: Optional[int] = None, world_local: Optional[int] 
         return []
     if world_local <= 1 or len(cores) < world_local:
         return cores
-    per = len(cores) // world_local
-    mine = cores[rank_local * per:(rank_local + 1) * per]
+    mine: List[int] = []
+    local = [c for c in _gpu_local_cores(rank_local if device_index is None else device_index) if c in set(cores)]
+    if local and len(local) < len(cores):
+        # the ranks whose GPUs share this locality set split it evenly, in local-rank order
+        sharers = [r for r in range(world_local) if sorted(c for c in _gpu_local_cores(r) if c in set(cores)) == local]
+        if rank_local in sharers and len(local) >= len(sharers):
+            per = len(local) // len(sharers)
+            k = sharers.index(rank_local)
+            mine = local[k * per:(k + 1) * per]
+    if not mine:
+        per = len(cores) // world_local
+        mine = cores[rank_local * per:(rank_local + 1) * per]
     try:
         os.sched_setaffinity(0, mine)
     except OSError:
