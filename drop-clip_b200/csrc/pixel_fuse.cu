@@ -676,7 +676,8 @@ namespace mma {
 
 using namespace dc::umma;
 
-constexpr int kStages = 3;
+constexpr int kStages = 6;
+constexpr int kLookahead = 4;    // cp.async groups in flight per loader thread before the oldest is published
 constexpr int kABytes = 4096;    // one plane of A: [2 k-halves][16 row groups][8 rows][16 B]
 constexpr int kBBytes = 8192;    // one plane of B: [2 k-groups][32 column groups][8 taps][16 B]   (N = 256)
 constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
@@ -937,7 +938,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
   uint64_t* tmem_empty = tmem_full + 2;       // [2]  4 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   unsigned* s_mask = reinterpret_cast<unsigned*>(tmem_slot + 2);  // [2 tile slots][4 warps]
-  int* s_nseg = reinterpret_cast<int*>(s_mask + 8);               // [2]
+  int* s_last = reinterpret_cast<int*>(s_mask + 8);               // [kStages] 1 when the stage holds the last segment of its (tile, chunk)
   float* s_trans = reinterpret_cast<float*>(smem + kStages * kStageBytes + 512);  // [4 epilogue warps][32][36] transposition blocks
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -971,7 +972,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
     const int r = threadIdx.x;
     int stage = 0;
     uint32_t phase = 0;
-    int pending = -1;  // stage whose cp.async group is in flight (lookahead of one stage)
+    int oldest = 0, n_pending = 0;  // ring of stages whose cp.async groups are still in flight
     int local_tile = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local_tile) {
       const int slot = local_tile & 1;
@@ -997,7 +998,6 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
         m[w] = s_mask[slot * 4 + w];
         nseg += __popc(m[w]);
       }
-      if (r == 0) s_nseg[slot] = nseg;  // read by the MMA warp after the first full barrier of this tile
       const int n_rows = (int)min(128u, n_pairs - (unsigned)tile * 128u);
       for (int c = 0; c < n_chunks; ++c) {
         int w = 0;
@@ -1019,6 +1019,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
             const int seg_key = __ldg(p.rec_key + (int64_t)tile * 128 + seg_start);
             uint8_t* st = stages + stage * kStageBytes;
             mbar_wait(empty + stage, phase ^ 1);
+            if (r == 0) s_last[stage] = (seg_end >= n_rows) ? 1 : 0;  // read by the MMA warp behind this stage's full barrier
             // A: my row's 16 weights, or zeros outside the segment
             const bool mine = r >= seg_start && r < seg_end;
             const int4 z = make_int4(0, 0, 0, 0);
@@ -1044,12 +1045,13 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
               cp_async16(bl + dst, p.plane_lo + src);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            if (pending >= 0) {  // the previous stage's copies have landed: publish it to the async proxy (MMA)
-              asm volatile("cp.async.wait_group 1;" ::: "memory");
+            if (++n_pending > kLookahead) {  // the oldest stage's copies have landed: publish it to the async proxy (MMA)
+              asm volatile("cp.async.wait_group %0;" ::"n"(kLookahead) : "memory");
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              mbar_arrive(full + pending);
+              mbar_arrive(full + oldest);
+              if (++oldest == kStages) oldest = 0;
+              --n_pending;
             }
-            pending = stage;
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
           if (next >= n_rows) break;
@@ -1057,10 +1059,11 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
         }
       }
     }
-    if (pending >= 0) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(full + pending);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (; n_pending > 0; --n_pending) {
+      mbar_arrive(full + oldest);
+      if (++oldest == kStages) oldest = 0;
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
@@ -1072,15 +1075,15 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
       uint32_t acc_phase = 0;
       int local_tile = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local_tile) {
-        int nseg = 1;
         for (int c = 0; c < n_chunks; ++c) {
           mbar_wait(tmem_empty + acc, acc_phase ^ 1);
           fence_after_sync();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-          for (int g = 0; g < nseg; ++g) {
+          bool last = false;
+          for (int g = 0; !last; ++g) {
             mbar_wait(full + stage, phase);
             fence_after_sync();
-            if (c == 0 && g == 0) nseg = *reinterpret_cast<volatile int*>(s_nseg + (local_tile & 1));
+            last = *reinterpret_cast<volatile int*>(s_last + stage) != 0;
             const uint32_t a_hi = smem_u32(stages + stage * kStageBytes), a_lo = a_hi + kABytes;
             const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + kBBytes;
             const uint64_t da_hi = smem_desc_noswizzle(a_hi, 2048, 128), da_lo = smem_desc_noswizzle(a_lo, 2048, 128);
