@@ -685,7 +685,7 @@ constexpr int kLoaderThreads = 128;
 constexpr int kMmaWarp = 4;
 constexpr int kEpiWarp0 = 8;
 constexpr int kThreadsMma = 384;
-constexpr int kSmemBytes = kStages * kStageBytes + 128 /*align*/ + 512 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue transposition*/;
+constexpr int kSmemBytes = kStages * kStageBytes + 128 /*align*/ + 512 /*barriers*/ + 1024 /*row keys*/ + 4 * 32 * 36 * 4 /*epilogue transposition*/;
 
 struct Footprints {
   int ph, pw, height, width;
@@ -939,7 +939,8 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   unsigned* s_mask = reinterpret_cast<unsigned*>(tmem_slot + 2);  // [2 tile slots][4 warps]
   int* s_last = reinterpret_cast<int*>(s_mask + 8);               // [kStages] 1 when the stage holds the last segment of its (tile, chunk)
-  float* s_trans = reinterpret_cast<float*>(smem + kStages * kStageBytes + 512);  // [4 epilogue warps][32][36] transposition blocks
+  int* s_keys = reinterpret_cast<int*>(smem + kStages * kStageBytes + 512);       // [2 tile slots][128] sort keys of the tile's rows
+  float* s_trans = reinterpret_cast<float*>(smem + kStages * kStageBytes + 512 + 1024);  // [4 epilogue warps][32][36] transposition blocks
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned n_pairs = *p.n_pairs;
@@ -990,6 +991,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
         a_lo1 = __ldg(ar + 3);
       }
       if (lane == 0) s_mask[slot * 4 + warp] = starts;
+      s_keys[slot * 128 + r] = key;  // a segment's key is read from here (a global load per stage sat on the critical path)
       asm volatile("bar.sync 2, 128;" ::: "memory");
       unsigned m[4];
       int nseg = 0;
@@ -1016,7 +1018,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
           }
           if (seg_start >= 0) {
             const int seg_end = next;
-            const int seg_key = __ldg(p.rec_key + (int64_t)tile * 128 + seg_start);
+            const int seg_key = s_keys[slot * 128 + seg_start];
             uint8_t* st = stages + stage * kStageBytes;
             mbar_wait(empty + stage, phase ^ 1);
             if (r == 0) s_last[stage] = (seg_end >= n_rows) ? 1 : 0;  // read by the MMA warp behind this stage's full barrier

@@ -691,8 +691,10 @@ class FusionEngine:
         `normalize`: return the final features of fuse_points (:266-268) instead of the sums (fused division)."""
         tv, ph, pw, dim = b.feats.shape
         kern = SIM_KERNELS[sim_kernel]
+        # the tensor-core path keeps 84 bytes of sort / operand records per (point, view) of the mask: batches beyond
+        # ~40 M mask elements (several full-size scenes at once) take the SIMT kernel instead of a multi-GB workspace
         use_mma = (dim in (512, 768, 1024) and b.total_points > 0 and os.environ.get("DC_PIXEL_PATH", "mma") != "simt"
-                   and b.feats.dtype == torch.float32)
+                   and b.feats.dtype == torch.float32 and int(b.off_host["mask"][-1]) <= 40_000_000)
         if use_mma:
             return self._pixel_fuse_mma(b, mask_u8, kern, norm_feat, normalize)
         sums = torch.empty((b.total_points, dim), dtype=torch.float32, device=b.device)
