@@ -677,15 +677,15 @@ namespace mma {
 using namespace dc::umma;
 
 constexpr int kStages = 6;
-constexpr int kLookahead = 4;    // cp.async groups in flight per loader thread before the oldest is published
 constexpr int kABytes = 4096;    // one plane of A: [2 k-halves][16 row groups][8 rows][16 B]
 constexpr int kBBytes = 8192;    // one plane of B: [2 k-groups][32 column groups][8 taps][16 B]   (N = 256)
 constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
 constexpr int kLoaderThreads = 128;
 constexpr int kMmaWarp = 4;
 constexpr int kEpiWarp0 = 8;
-constexpr int kThreadsMma = 384;
-constexpr int kSmemBytes = kStages * kStageBytes + 128 /*align*/ + 512 /*barriers*/ + 1024 /*row keys*/ + 4 * 32 * 36 * 4 /*epilogue transposition*/;
+constexpr int kEpiWarps = 8;       // two groups of four (TMEM lane quarters): group h owns columns [128 h, 128 h + 128) of a chunk
+constexpr int kThreadsMma = (kEpiWarp0 + kEpiWarps) * 32;
+constexpr int kSmemBytes = kStages * kStageBytes + 128 /*align*/ + 512 /*barriers*/ + 1024 /*row keys*/ + kEpiWarps * 32 * 36 * 4 /*epilogue transposition*/;
 
 struct Footprints {
   int ph, pw, height, width;
@@ -907,6 +907,14 @@ __host__ __device__ constexpr uint32_t idesc_f16_f32_bmn(int m, int n) {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+// 16 bytes from global memory, or 16 zero bytes when !take (src-size 0: nothing is read)
+__device__ __forceinline__ void cp_async16_or_zero(void* smem_dst, const void* gsrc, bool take) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(take ? 16 : 0) : "memory");
+}
+// arrival on the mbarrier once all cp.async of this thread issued so far have landed (counts against the expected arrivals)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -950,12 +958,12 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full + s, kLoaderThreads);
+      mbar_init(full + s, kLoaderThreads + 1);  // 128 cp.async completions + thread 0's arrival behind the segment flag
       mbar_init(empty + s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full + a, 1);
-      mbar_init(tmem_empty + a, 4);
+      mbar_init(tmem_empty + a, kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -973,23 +981,29 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
     const int r = threadIdx.x;
     int stage = 0;
     uint32_t phase = 0;
-    int oldest = 0, n_pending = 0;  // ring of stages whose cp.async groups are still in flight
+
     int local_tile = 0;
+    // rows of a tile: sort key, the key of the row before (segment starts) and the 16 tap weights (hi / lo). They are
+    // fetched one tile AHEAD, so that a tile's first stage is not issued behind two dependent global-load latencies.
+    struct Rows { int key, prev; };
+    auto fetch_rows = [&](int tile) -> Rows {
+      Rows t{-1, -2};
+      const unsigned row = (unsigned)tile * 128u + (unsigned)r;
+      if (tile < n_tiles && row < n_pairs) {
+        t.key = __ldg(p.rec_key + row);
+        if (r != 0) t.prev = __ldg(p.rec_key + row - 1);
+      }
+      return t;
+    };
+    Rows next = fetch_rows(blockIdx.x);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local_tile) {
       const int slot = local_tile & 1;
-      const unsigned row = (unsigned)tile * 128u + (unsigned)r;
-      const bool valid = row < n_pairs;
-      const int key = valid ? __ldg(p.rec_key + row) : -1;
-      const int prev = (r == 0 || !valid) ? -2 : __ldg(p.rec_key + row - 1);
-      const unsigned starts = __ballot_sync(0xffffffffu, valid && key != prev);
-      int4 a_hi0 = make_int4(0, 0, 0, 0), a_hi1 = a_hi0, a_lo0 = a_hi0, a_lo1 = a_hi0;
-      if (valid) {
-        const int4* ar = reinterpret_cast<const int4*>(p.arec + (int64_t)row * 32);
-        a_hi0 = __ldg(ar);
-        a_hi1 = __ldg(ar + 1);
-        a_lo0 = __ldg(ar + 2);
-        a_lo1 = __ldg(ar + 3);
-      }
+      const Rows cur = next;
+      next = fetch_rows(tile + gridDim.x);
+      const int key = cur.key;
+      const unsigned starts = __ballot_sync(0xffffffffu, key >= 0 && key != cur.prev);
+      // my row's 16 tap weights (hi, lo) in global memory; rows past the end are never inside a segment
+      const __half* my_arec = p.arec + (int64_t)(key >= 0 ? (unsigned)tile * 128u + (unsigned)r : 0u) * 32;
       if (lane == 0) s_mask[slot * 4 + warp] = starts;
       s_keys[slot * 128 + r] = key;  // a segment's key is read from here (a global load per stage sat on the critical path)
       asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -1021,15 +1035,18 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
             const int seg_key = s_keys[slot * 128 + seg_start];
             uint8_t* st = stages + stage * kStageBytes;
             mbar_wait(empty + stage, phase ^ 1);
-            if (r == 0) s_last[stage] = (seg_end >= n_rows) ? 1 : 0;  // read by the MMA warp behind this stage's full barrier
-            // A: my row's 16 weights, or zeros outside the segment
+            if (r == 0) {  // read by the MMA warp behind this stage's full barrier (a plain arrival: release)
+              s_last[stage] = (seg_end >= n_rows) ? 1 : 0;
+              mbar_arrive(full + stage);
+            }
+            // A: my row's 16 weights, or zeros outside the segment - also by cp.async (zero-fill form), so that the loader
+            // never touches the stage through the generic proxy and never has to wait for its own copies
             const bool mine = r >= seg_start && r < seg_end;
-            const int4 z = make_int4(0, 0, 0, 0);
             uint8_t* arow = st + (r >> 3) * 128 + (r & 7) * 16;
-            *reinterpret_cast<int4*>(arow) = mine ? a_hi0 : z;
-            *reinterpret_cast<int4*>(arow + 2048) = mine ? a_hi1 : z;
-            *reinterpret_cast<int4*>(arow + kABytes) = mine ? a_lo0 : z;
-            *reinterpret_cast<int4*>(arow + kABytes + 2048) = mine ? a_lo1 : z;
+            cp_async16_or_zero(arow, my_arec, mine);
+            cp_async16_or_zero(arow + 2048, my_arec + 8, mine);
+            cp_async16_or_zero(arow + kABytes, my_arec + 16, mine);
+            cp_async16_or_zero(arow + kABytes + 2048, my_arec + 24, mine);
             // B: 16 taps x 256 channels of both planes, 16 bytes per copy
             const int vk = seg_key / p.nfp, f = seg_key - vk * p.nfp;
             const int v_glob = vk % p.total_views;
@@ -1046,14 +1063,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
               cp_async16(bh + dst, p.plane_hi + src);
               cp_async16(bl + dst, p.plane_lo + src);
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            if (++n_pending > kLookahead) {  // the oldest stage's copies have landed: publish it to the async proxy (MMA)
-              asm volatile("cp.async.wait_group %0;" ::"n"(kLookahead) : "memory");
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              mbar_arrive(full + oldest);
-              if (++oldest == kStages) oldest = 0;
-              --n_pending;
-            }
+            cp_async_arrive_noinc(full + stage);  // arrives when this thread's copies of the stage have landed
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
           if (next >= n_rows) break;
@@ -1061,12 +1071,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
         }
       }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (; n_pending > 0; --n_pending) {
-      mbar_arrive(full + oldest);
-      if (++oldest == kStages) oldest = 0;
-    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -1084,6 +1089,8 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
           bool last = false;
           for (int g = 0; !last; ++g) {
             mbar_wait(full + stage, phase);
+            // the stage was written by the loaders' cp.async (generic proxy); the MMA reads it through the async proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             fence_after_sync();
             last = *reinterpret_cast<volatile int*>(s_last + stage) != 0;
             const uint32_t a_hi = smem_u32(stages + stage * kStageBytes), a_lo = a_hi + kABytes;
@@ -1102,31 +1109,37 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue: thread <-> row =====================
+    // ===================== epilogue: thread <-> row, warp group h <-> column half h of the chunk =====================
     const int quarter = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;
     const int r = quarter * 32 + lane;
+    float* tb = s_trans + (warp - kEpiWarp0) * (32 * 36);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const unsigned row = (unsigned)tile * 128u + (unsigned)r;
       const bool valid = row < n_pairs;
-      const int point = valid ? __ldg(p.rec_point + row) : 0;
+      const int point = valid ? __ldg(p.rec_point + row) : -1;
       const float sc = (kAccum && valid) ? __ldg(p.scale + row) : 0.f;
       float ss = 0.f;
       for (int c = 0; c < n_chunks; ++c) {
         mbar_wait(tmem_full + acc, acc_phase);
         fence_after_sync();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
-#pragma unroll 1
-        for (int cc = 0; cc < 8; ++cc) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + (uint32_t)(cc * 32), v);
-          tmem_ld_wait();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + half * 128);
+        const int col0 = c * 256 + half * 128;
+        // four 32-column blocks, the TMEM load of block cc + 1 in flight while block cc is processed
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(taddr, va);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t(&v)[32] = (cc & 1) ? vb : va;
+          uint32_t(&nx)[32] = (cc & 1) ? va : vb;
+          if (cc + 1 < 4) tmem_ld_32x32(taddr + (uint32_t)((cc + 1) * 32), nx);
           if (kAccum) {
             // thread = row out of TMEM, but a warp-wide red of one row segment per thread would touch 32 half-used sectors:
             // the 32 x 32 block goes through shared memory (row stride 36 floats) and comes back with 8 lanes per row,
             // so one red instruction adds 4 rows x 128 contiguous bytes (16 full sectors)
-            float* tb = s_trans + (warp - kEpiWarp0) * (32 * 36);
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 32; i += 4)
@@ -1136,21 +1149,22 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = i * 4 + (lane >> 3);
-              const int pt = __shfl_sync(0xffffffffu, valid ? point : -1, rr);
+              const int pt = __shfl_sync(0xffffffffu, point, rr);
               const float4 q = *reinterpret_cast<const float4*>(tb + rr * 36 + (lane & 7) * 4);
-              if (pt >= 0) red_add_v4(p.out + (int64_t)pt * p.dim + c * 256 + cc * 32 + (lane & 7) * 4, q.x, q.y, q.z, q.w);
+              if (pt >= 0) red_add_v4(p.out + (int64_t)pt * p.dim + col0 + cc * 32 + (lane & 7) * 4, q.x, q.y, q.z, q.w);
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) ss = fmaf(__uint_as_float(v[i]), __uint_as_float(v[i]), ss);
           }
+          if (cc + 1 < 4) tmem_ld_wait();
         }
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (!kAccum && valid) p.norm2[row] = ss;
+      if (!kAccum && valid) atomicAdd(p.norm2 + row, ss);  // the two column halves of a row meet here (norm2 starts at zero)
     }
   }
 
@@ -1445,7 +1459,10 @@ int dc_pixel_fuse_mma(const double* points, const int64_t* point_off, const int6
   DC_CUDA(cudaFuncSetAttribute(mma::pixel_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mma::kSmemBytes));
   const int64_t max_tiles = dc::ceil_div<int64_t>(mask_elems, 128);
   const unsigned mgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(max_tiles, dc::sm_count()));
-  if (norm_feat) mma::pixel_mma_kernel<false><<<mgrid, mma::kThreadsMma, mma::kSmemBytes, st>>>(mp);
+  if (norm_feat) {
+    DC_CUDA(cudaMemsetAsync(norm2, 0, (size_t)mask_elems * sizeof(float), st));
+    mma::pixel_mma_kernel<false><<<mgrid, mma::kThreadsMma, mma::kSmemBytes, st>>>(mp);
+  }
   const unsigned wgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(dc::ceil_div<int64_t>(mask_elems, kThreads), (int64_t)dc::sm_count() * 16));
   mma::pair_weight_kernel<<<wgrid, kThreads, 0, st>>>(p, fp, n_scenes, rec_point, rec_pix, rec_key, total, norm2, scale);
   mma::pixel_mma_kernel<true><<<mgrid, mma::kThreadsMma, mma::kSmemBytes, st>>>(mp);
