@@ -9,7 +9,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdropclip.so")
+LIB_PATH = os.environ.get("DROPCLIP_LIB") or os.path.join(HERE, "libdropclip.so")  # DROPCLIP_LIB: an experimental build
 
 DC_F16, DC_F32, DC_U8, DC_I32, DC_I64, DC_F64 = 0, 1, 2, 3, 4, 5
 DC_SIM_NONE, DC_SIM_MAX, DC_SIM_MEAN = 0, 1, 2

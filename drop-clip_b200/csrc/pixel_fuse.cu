@@ -685,7 +685,7 @@ constexpr int kMmaWarp = 4;
 constexpr int kEpiWarp0 = 8;
 constexpr int kEpiWarps = 8;       // two groups of four (TMEM lane quarters): group h owns columns [128 h, 128 h + 128) of a chunk
 constexpr int kThreadsMma = (kEpiWarp0 + kEpiWarps) * 32;
-constexpr int kSmemBytes = kStages * kStageBytes + 128 /*align*/ + 512 /*barriers*/ + 1024 /*row keys*/ + kEpiWarps * 32 * 36 * 4 /*epilogue transposition*/;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*row keys*/ + kEpiWarps * 32 * 36 * 4 /*epilogue transposition*/;
 
 struct Footprints {
   int ph, pw, height, width;
@@ -900,6 +900,17 @@ __device__ __forceinline__ uint64_t smem_desc_noswizzle(uint32_t smem_addr, uint
   d |= (uint64_t)1 << 46;  // version
   return d;                // layout type 0 = no swizzle
 }
+// MN-major, SWIZZLE_128B:  ((8, 8, m), (8, k)) : ((1 elem, 16 B, LBO), (128 B, SBO)) with Swizzle<3,4,3> - LBO between the
+// 64-element atoms along N, SBO between the 8-row groups along K
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;  // version
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
 // fp32 accumulator, fp16 A (K-major) and B (MN-major: bit 16)
 __host__ __device__ constexpr uint32_t idesc_f16_f32_bmn(int m, int n) {
   return (1u << 4) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -937,7 +948,7 @@ template <bool kAccum>
 __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((128u - (raw_addr & 127u)) & 127u);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B operand atoms need 1024-byte alignment
   uint8_t* stages = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* full = bars;                 // [kStages]  128 loader arrivals
@@ -1059,7 +1070,10 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
               const int t = idx >> 5, g8 = idx & 31;
               const int cy = min(max(iy0 - 1 + (t >> 2), 0), p.ph - 1), cx = min(max(ix0 - 1 + (t & 3), 0), p.pw - 1);
               const int64_t src = ((int64_t)v_glob * ncell + cy * p.pw + cx) * p.dim + c * 256 + g8 * 8;
-              const int dst = (t >> 3) * 4096 + g8 * 128 + (t & 7) * 16;
+              // MN-major SWIZZLE_128B: atoms of 8 taps x 64 channels (8 rows of 128 B, 16-byte chunk index XOR tap row),
+              // four atoms along N (1024 B apart), two tap groups (4096 B apart). The no-swizzle core-matrix layout put the
+              // 32 column groups of a tap row 128 B apart - every operand fetch of the tensor core hit the same banks.
+              const int dst = (t >> 3) * 4096 + (g8 >> 3) * 1024 + (t & 7) * 128 + (((g8 & 7) ^ (t & 7)) << 4);
               cp_async16(bh + dst, p.plane_hi + src);
               cp_async16(bl + dst, p.plane_lo + src);
             }
@@ -1090,13 +1104,15 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
           for (int g = 0; !last; ++g) {
             mbar_wait(full + stage, phase);
             // the stage was written by the loaders' cp.async (generic proxy); the MMA reads it through the async proxy
+#ifndef DC_EXPERIMENT_NO_PROXY_FENCE
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
             fence_after_sync();
             last = *reinterpret_cast<volatile int*>(s_last + stage) != 0;
             const uint32_t a_hi = smem_u32(stages + stage * kStageBytes), a_lo = a_hi + kABytes;
             const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + kBBytes;
             const uint64_t da_hi = smem_desc_noswizzle(a_hi, 2048, 128), da_lo = smem_desc_noswizzle(a_lo, 2048, 128);
-            const uint64_t db_hi = smem_desc_noswizzle(b_hi, 4096, 128), db_lo = smem_desc_noswizzle(b_lo, 4096, 128);
+            const uint64_t db_hi = smem_desc_mn_sw128(b_hi, 1024, 4096), db_lo = smem_desc_mn_sw128(b_lo, 1024, 4096);
             mma_f16_ss(d_tmem, da_hi, db_hi, idesc, g ? 1u : 0u);
             mma_f16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
             mma_f16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
