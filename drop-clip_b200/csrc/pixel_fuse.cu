@@ -1201,7 +1201,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1) pixel_mma_kernel(const MmaPara
 __global__ void __launch_bounds__(kThreads) pair_weight_kernel(PixParams p, Footprints fp, int n_scenes, const int* __restrict__ rec_point,
                                                                const uint32_t* __restrict__ rec_pix, const int* __restrict__ rec_key,
                                                                const unsigned* __restrict__ n_pairs_dev, const float* __restrict__ norm2,
-                                                               float* __restrict__ scale) {
+                                                               float* __restrict__ scale, float* __restrict__ den) {
   const unsigned n_pairs = *n_pairs_dev;
   const int64_t hw = (int64_t)p.height * p.width;
   for (unsigned pair = blockIdx.x * kThreads + threadIdx.x; pair < n_pairs; pair += gridDim.x * kThreads) {
@@ -1266,11 +1266,30 @@ __global__ void __launch_bounds__(kThreads) pair_weight_kernel(PixParams p, Foot
       }
     }
     scale[pair] = p.norm_feat ? weight / nrm : weight;  // (f / |f|) * weight; 0 / 0 = NaN like the reference
+    if (den) atomicAdd(den + __ldg(rec_point + pair), weight);  // denominator of fuse_points :266-268 (sum of weights / view count)
+  }
+}
+
+// normalize: the division of fuse_points is folded into the pair scales (sum_v s_v f_v / den = sum_v (s_v / den) f_v), and the
+// rows of points nobody sees become 0 / 0 = NaN like the separate division pass would leave them
+__global__ void __launch_bounds__(kThreads) pair_scale_div_kernel(const int* __restrict__ rec_point, const unsigned* __restrict__ n_pairs_dev,
+                                                                  const float* __restrict__ den, float* __restrict__ scale) {
+  const unsigned n_pairs = *n_pairs_dev;
+  for (unsigned pair = blockIdx.x * kThreads + threadIdx.x; pair < n_pairs; pair += gridDim.x * kThreads)
+    scale[pair] = scale[pair] / __ldg(den + __ldg(rec_point + pair));
+}
+__global__ void __launch_bounds__(kThreads) nan_unseen_rows_kernel(const float* __restrict__ den, int64_t total_points, int dim,
+                                                                   float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t i = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); i < total_points; i += (int64_t)gridDim.x * kWarps) {
+    if (__ldg(den + i) != 0.f) continue;  // (a NaN denominator already made the row NaN through its scales)
+    float* row = out + i * dim;
+    for (int c = lane; c < dim; c += 32) row[c] = __int_as_float(0x7fc00000);
   }
 }
 
 struct Workspace {
-  size_t dots, pix, counts, sums, total, rec_point, rec_pix, rec_key, arec, norm2, scale, plane_hi, plane_lo, bytes;
+  size_t dots, pix, counts, sums, total, rec_point, rec_pix, rec_key, arec, norm2, scale, den, plane_hi, plane_lo, bytes;
   int64_t n_keys, n_scan_blocks;
 };
 constexpr int kMaxRegions = 32;
@@ -1292,6 +1311,7 @@ Workspace layout(int64_t total_views, int64_t mask_elems, int ph, int pw, int di
   w.arec = take((size_t)pairs * 64);
   w.norm2 = take((size_t)pairs * 4);
   w.scale = take((size_t)pairs * 4);
+  w.den = take((size_t)pairs * 4);  // per point (<= pairs)
   w.plane_hi = take((size_t)total_views * ph * pw * dim * 2);
   w.plane_lo = take((size_t)total_views * ph * pw * dim * 2);
   w.bytes = off;
@@ -1480,12 +1500,16 @@ int dc_pixel_fuse_mma(const double* points, const int64_t* point_off, const int6
     mma::pixel_mma_kernel<false><<<mgrid, mma::kThreadsMma, mma::kSmemBytes, st>>>(mp);
   }
   const unsigned wgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(dc::ceil_div<int64_t>(mask_elems, kThreads), (int64_t)dc::sm_count() * 16));
-  mma::pair_weight_kernel<<<wgrid, kThreads, 0, st>>>(p, fp, n_scenes, rec_point, rec_pix, rec_key, total, norm2, scale);
+  float* den = normalize ? reinterpret_cast<float*>(ws + w.den) : nullptr;
+  if (den) DC_CUDA(cudaMemsetAsync(den, 0, (size_t)total_points * sizeof(float), st));
+  mma::pair_weight_kernel<<<wgrid, kThreads, 0, st>>>(p, fp, n_scenes, rec_point, rec_pix, rec_key, total, norm2, scale, den);
+  if (den) mma::pair_scale_div_kernel<<<wgrid, kThreads, 0, st>>>(rec_point, total, den, scale);
   mma::pixel_mma_kernel<true><<<mgrid, mma::kThreadsMma, mma::kSmemBytes, st>>>(mp);
+  if (den) {
+    const unsigned ngrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(dc::ceil_div<int64_t>(total_points, kWarps), (int64_t)dc::sm_count() * 16));
+    mma::nan_unseen_rows_kernel<<<ngrid, kThreads, 0, st>>>(den, total_points, dim, out_sum);
+  }
   DC_LAUNCH_CHECK();
-  if (normalize)
-    return dc_pixel_normalize(out_sum, point_off, view_off, mask_off, visible, sim_kernel != DC_SIM_NONE ? out_weight : nullptr, n_scenes,
-                              max_points_per_scene, dim, stream);
   return DC_OK;
 }
 
