@@ -151,6 +151,49 @@ __global__ void __launch_bounds__(kThreads) patch_query_dots_kernel(PixParams p)
   }
 }
 
+// The same table for the CLIP widths (dim = 32 * kPer), four patch cells per warp: a query chunk is loaded once per four
+// cells and the four fp64 chains (and their shuffle reductions) overlap. Same per-lane summation order as above, so the
+// table is bit-identical. (The one-cell version is latency-bound: 0.44 ms for 73 x 768 cells x 21 queries.)
+template <int kPer>
+__global__ void __launch_bounds__(kThreads) patch_query_dots4_kernel(PixParams p) {
+  const int scene = blockIdx.y;
+  const int64_t v0 = p.view_off[scene];
+  const int n_views = (int)(p.view_off[scene + 1] - v0);
+  const int n_q = (int)(p.query_off[scene + 1] - p.query_off[scene]);
+  const float* q = p.queries + p.query_off[scene] * p.dim;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_cells = (int64_t)p.ph * p.pw, n_rows = n_cells * n_views;
+  for (int64_t r0 = ((int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5)) * 4; r0 < n_rows; r0 += (int64_t)gridDim.x * kWarps * 4) {
+    float t[4][kPer];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int64_t r = r0 + c < n_rows ? r0 + c : n_rows - 1;  // a ragged last group repeats the last row (not stored)
+      const float* row = p.patch + (v0 * n_cells + r) * p.dim;
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) t[c][k] = __ldg(row + k * 32 + lane);
+    }
+    for (int o = 0; o < n_q; ++o) {
+      const float* qo = q + (int64_t)o * p.dim;
+      double d[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        const double qv = (double)__ldg(qo + k * 32 + lane);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d[c] = fma((double)t[c][k], qv, d[c]);
+      }
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d[c] += __shfl_xor_sync(0xffffffffu, d[c], sh);
+      }
+      if (lane < 4 && r0 + lane < n_rows) {
+        const double mine = lane == 0 ? d[0] : lane == 1 ? d[1] : lane == 2 ? d[2] : d[3];
+        p.dots[(v0 * n_cells + r0 + lane) * p.q_stride + o] = mine;
+      }
+    }
+  }
+}
+
 // Similarity weights in fp64. The weight of a visible (point, view) is clip(pos - max|mean(neg), 1e-6) of the
 // similarities of its (normalised) interpolated feature with the scene's queries (calculate_sim,
 // feature_fusion.py:65-73,182-196). On surfaces whose best two queries tie, pos - neg is a difference of two numbers
@@ -1471,8 +1514,10 @@ int dc_pixel_fuse_mma(const double* points, const int64_t* point_off, const int6
     p.q_stride = query_stride(max_queries_per_scene);
     if (total_views > 0 && max_queries_per_scene > 0) {
       const int64_t rows = (int64_t)max_views_per_scene * patch_h * patch_w;
-      dim3 dgrid(blocks_for(rows, n_scenes), (unsigned)n_scenes);
-      patch_query_dots_kernel<<<dgrid, kThreads, 0, st>>>(p);
+      dim3 dgrid(blocks_for((rows + 3) / 4, n_scenes), (unsigned)n_scenes);
+      if (dim == 768) patch_query_dots4_kernel<24><<<dgrid, kThreads, 0, st>>>(p);
+      else if (dim == 512) patch_query_dots4_kernel<16><<<dgrid, kThreads, 0, st>>>(p);
+      else patch_query_dots4_kernel<32><<<dgrid, kThreads, 0, st>>>(p);
       DC_LAUNCH_CHECK();
     }
   }
