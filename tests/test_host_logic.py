@@ -213,11 +213,19 @@ def test_host_staging_helpers_copy_and_narrow():
     assert lib.dc_host_gather_copy(None, 1, 4, None, 1) != 0  # null pointers are rejected, not dereferenced
 
 
-def test_committed_bench_line_has_the_contract_keys():
-    """profiles/r01_bench_final.json is a line printed by bench.py on a B200; its shape is the driver's contract."""
+@pytest.mark.parametrize("name", ["r01_bench_final.json", "r02_bench_final.json", "r02_bench_n2.json", "r02_bench_n4.json"])
+def test_committed_bench_line_has_the_contract_keys(name):
+    """profiles/rNN_bench_*.json are lines printed by bench.py on B200s; their shape is the driver's contract."""
     import json
-    path = os.path.join(ROOT, "profiles", "r01_bench_final.json")
+    path = os.path.join(ROOT, "profiles", name)
     d = json.loads(open(path).read())
+    if d["n_gpus"] > 1:
+        d.setdefault("cpu_baseline", None)
+        assert d["cpu_baseline"] is None  # rank 0 at N = 1 only
+        d["cpu_baseline"] = {"value": 0, "unit": "", "cores": 0, "kind": "port", "sample": ""}
+    if name.startswith("r02"):
+        assert d["e2e"]["bound"]["kind"] == "pcie_h2d" and 0 < d["e2e"]["bound"]["frac_of_bound"] <= 1.05
+        assert d["distinct_scene_job"]["scenes"] in (256, 1000) and d["resident_full_output"]["mask_dtype"] == "int64"
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k
