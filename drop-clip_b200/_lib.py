@@ -22,6 +22,7 @@ SIGNATURES = {
     "dc_abi_version": (c_int, []),
     "dc_last_error": (c_char_p, []),
     "dc_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
+    "dc_set_stream_overlap": (c_int, [c_int]),
     "dc_project_visibility": (c_int, [P, P, P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_double, P, c_int, P, P,
                                       c_int, P, P]),
     "dc_visibility_sorted_workspace": (c_size_t, [c_int64, c_int, c_int]),

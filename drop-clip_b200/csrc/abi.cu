@@ -31,9 +31,20 @@ int sm_count() {
   return cached;
 }
 
+namespace {
+int g_stream_overlap = 1;
+}
+bool stream_overlap() { return g_stream_overlap != 0; }
+
 }  // namespace dc
 
 extern "C" {
+
+int dc_set_stream_overlap(int on) {
+  const int prev = dc::g_stream_overlap;
+  dc::g_stream_overlap = on ? 1 : 0;
+  return prev;
+}
 
 int dc_abi_version(void) { return DC_ABI_VERSION; }
 

@@ -8,7 +8,10 @@
 // Roofline: HBM-bound, reads each pixel once (8 B/pixel for the reference's int64 maps, 1 B for
 // uint8 maps). Instance maps are piecewise constant, so a thread run-length-compresses what it
 // reads and touches the shared-memory histogram only when the id changes.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "umma.cuh"  // mbarrier helpers
 
 namespace {
 
@@ -121,6 +124,197 @@ __global__ void __launch_bounds__(kThreads) seg_histogram_kernel(const T* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ring variant for the reference's int64 maps (the dominant kernel of the object-level step).
+//
+// The histogram pass is HBM-bound and needs few issue slots; the visibility filter that shares the step
+// is issue-bound and needs little HBM. The engine therefore runs the two on different streams, and this
+// kernel is shaped to live BESIDE the filter on every SM instead of alternating with it:
+//   * persistent, one CTA per SM, few warps: two filter CTAs (2 x 256 x 80 registers, 2 x 33 KB) fit next to it;
+//   * the bytes in flight that a streaming kernel needs (~50 KB per SM at 7 TB/s) come from shared-memory
+//     rings filled by 1-D bulk copies (cp.async.bulk -> mbarrier complete_tx, L2 evict-first), not from the
+//     registers of hundreds of resident threads;
+//   * every warp runs its own ring (2 KB units, `depth` slots, its lane 0 is the producer), so a warp that
+//     meets an object boundary (the slow, per-pixel path) does not hold up the other warps;
+//   * the CTA owns a contiguous range of units of the whole batch, interleaved over its warps, and flushes its
+//     shared-memory histogram whenever the range crosses into the next view (global atomics: a view may be split
+//     between two CTAs).
+// Counting is the same run-length scheme as above. A lane owns 64 contiguous bytes = eight neighbouring pixels:
+// "all eight equal" is an XOR/OR tree on the ALU, then one 64-bit compare against the current run.
+constexpr int kUnit = 2048;  // bytes per warp unit: 32 lanes x 64 B
+constexpr int kRingDepthDefault = 3;
+
+__device__ __forceinline__ void bulk_load_evict_first(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                                      uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dc::umma::smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(dc::umma::smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+template <int kRingWarps, int kMinCtas>
+__global__ void __launch_bounds__(kRingWarps * 32, kMinCtas)
+seg_histogram_ring_kernel(const long long* __restrict__ seg, int64_t bytes_per_view, int units_per_view, int64_t total_units,
+                          int nbins, int depth, int flags, uint32_t* __restrict__ counts,
+                          unsigned long long* __restrict__ outside_out) {
+  using namespace dc::umma;
+  constexpr int kRingThreads = kRingWarps * 32;
+  extern __shared__ __align__(128) unsigned char s_ring[];  // [warps][depth][2 KB], histogram, full[warps][depth]
+  const size_t ring_bytes = (size_t)kRingWarps * depth * kUnit;
+  unsigned* s_hist = reinterpret_cast<unsigned*>(s_ring + ring_bytes);
+  uint64_t* full_all = reinterpret_cast<uint64_t*>(s_ring + ring_bytes + ((nbins * 4 + 15) & ~15));
+  const int64_t g0 = total_units * blockIdx.x / gridDim.x, g1 = total_units * (blockIdx.x + 1) / gridDim.x;
+  if (g1 <= g0) return;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRingWarps * depth; ++i) mbar_init(full_all + i, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < nbins; i += kRingThreads) s_hist[i] = 0;
+  __syncthreads();
+
+  const int64_t v_first = g0 / units_per_view, v_last = (g1 - 1) / units_per_view;
+  const int j_first = (int)(g0 - v_first * units_per_view);
+  const int last_bytes = (int)(bytes_per_view - (int64_t)(units_per_view - 1) * kUnit);  // of a view's last unit
+  auto view_end = [&](int64_t v) -> int {  // end of this CTA's unit range inside view v
+    const int64_t e = g1 - v * units_per_view;
+    return e < units_per_view ? (int)e : units_per_view;
+  };
+  unsigned char* my_ring = s_ring + (size_t)w * depth * kUnit;
+  uint64_t* full = full_all + w * depth;
+  const char* base = reinterpret_cast<const char*>(seg);
+
+  // producer state (lane 0): the warp's next unit to load = (pv, pj), into slot pslot
+  uint64_t policy = 0;
+  int64_t pv = v_first;
+  int pb = view_end(pv), pj = j_first + w, pslot = 0;
+  auto skip_empty_views = [&]() {
+    while (pj >= pb && pv < v_last) {
+      ++pv;
+      pb = view_end(pv);
+      pj = w;
+    }
+  };
+  auto issue = [&]() {
+    const uint32_t bytes = (uint32_t)(pj == units_per_view - 1 ? last_bytes : kUnit);
+    const char* src = base + pv * bytes_per_view + (int64_t)pj * kUnit;
+    mbar_expect_tx(full + pslot, bytes);
+    if (flags & 2)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(my_ring + pslot * kUnit)), "l"(src), "r"(bytes), "r"(smem_u32(full + pslot)) : "memory");
+    else
+      bulk_load_evict_first(my_ring + pslot * kUnit, src, bytes, full + pslot, policy);
+    pslot = (pslot == depth - 1) ? 0 : pslot + 1;
+    pj += kRingWarps;
+    skip_empty_views();
+  };
+  if (lane == 0) {
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    skip_empty_views();
+    for (int d = 0; d < depth && pj < pb; ++d) issue();
+  }
+
+  RunAcc run{-1, 0};
+  int slot = 0;
+  uint32_t parity = 0;
+  // a lane's four 16-byte reads of its 64 bytes are rotated by lane so that the eight lanes of a shared-memory phase
+  // fall into eight different 16-byte bank groups
+  int idx[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) idx[k] = 4 * lane + ((k + (lane >> 1)) & 3);
+
+  for (int64_t v = v_first; v <= v_last; ++v) {
+    const int b = view_end(v);
+    unsigned long long* outside = outside_out + 4 * v;
+    for (int j = (v == v_first ? j_first : 0) + w; j < b; j += kRingWarps) {
+      mbar_wait(full + slot, parity);
+      const int n_vec = (j == units_per_view - 1 ? last_bytes : kUnit) >> 4;
+      const int4* unit = reinterpret_cast<const int4*>(my_ring + slot * kUnit);
+      int4 r[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r[k] = unit[idx[k] < n_vec ? idx[k] : 0];
+      if (flags & 1) {
+        run.cnt += (unsigned)(r[0].x ^ r[1].y ^ r[2].z ^ r[3].w) & 1u;
+      } else if (n_vec == kUnit / 16) {
+        const unsigned lo0 = (unsigned)r[0].x, hi0 = (unsigned)r[0].y;
+        unsigned d = ((unsigned)r[0].z ^ lo0) | ((unsigned)r[0].w ^ hi0);
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+          d |= ((unsigned)r[k].x ^ lo0) | ((unsigned)r[k].y ^ hi0) | ((unsigned)r[k].z ^ lo0) | ((unsigned)r[k].w ^ hi0);
+        if (d == 0) {  // eight equal ids
+          const long long id = (long long)(((unsigned long long)hi0 << 32) | lo0);
+          if (id != run.cur) {
+            flush_run(run, s_hist, outside, nbins);
+            run.cur = id;
+            run.cnt = 0;
+          }
+          run.cnt += 8;
+        } else {
+          // an object boundary inside the lane's eight pixels. The other lanes of the warp wait for this path, so it is
+          // kept short and free of dependent chains: close the run, then one shared-memory atomic per pixel.
+          flush_run(run, s_hist, outside, nbins);
+          run.cur = -1;
+          run.cnt = 0;
+          const unsigned hi_any = (unsigned)r[0].y | (unsigned)r[0].w | (unsigned)r[1].y | (unsigned)r[1].w | (unsigned)r[2].y |
+                                  (unsigned)r[2].w | (unsigned)r[3].y | (unsigned)r[3].w;
+          const unsigned lo_max = max(max(max((unsigned)r[0].x, (unsigned)r[0].z), max((unsigned)r[1].x, (unsigned)r[1].z)),
+                                      max(max((unsigned)r[2].x, (unsigned)r[2].z), max((unsigned)r[3].x, (unsigned)r[3].z)));
+          if (hi_any == 0 && lo_max < (unsigned)nbins) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              atomicAdd(s_hist + (unsigned)r[k].x, 1u);
+              atomicAdd(s_hist + (unsigned)r[k].z, 1u);
+            }
+          } else {  // ids outside the histogram (negative background, id >= nbins): the general path
+#pragma unroll
+            for (int k = 0; k < 4; ++k) consume_vector<long long>(r[k], run, s_hist, outside, nbins);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (idx[k] < n_vec) consume_vector<long long>(r[k], run, s_hist, outside, nbins);
+      }
+      // every lane has used its registers, so the shared-memory reads of the slot are complete: refill it
+      __syncwarp();
+      if (lane == 0 && pj < pb) issue();
+      if (++slot == depth) {
+        slot = 0;
+        parity ^= 1u;
+      }
+    }
+    // end of the view (or of the CTA's range): all warps flush into the view's global row
+    flush_run(run, s_hist, outside, nbins);
+    run.cur = -1;
+    run.cnt = 0;
+    __syncthreads();
+    for (int bin = threadIdx.x; bin < nbins; bin += kRingThreads) {
+      const unsigned t = s_hist[bin];
+      if (t) {
+        atomicAdd(counts + v * nbins + bin, t);
+        s_hist[bin] = 0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int kRingWarps, int kMinCtas>
+int launch_ring(const void* seg, int64_t bytes_per_view, int64_t total_views, int nbins, int depth, int flags, int carve,
+                uint32_t* counts, uint64_t* outside, cudaStream_t st) {
+  auto kernel = seg_histogram_ring_kernel<kRingWarps, kMinCtas>;
+  const int upv = (int)dc::ceil_div<int64_t>(bytes_per_view, kUnit);
+  const size_t smem = (size_t)kRingWarps * depth * kUnit + ((sizeof(unsigned) * nbins + 15) & ~(size_t)15) +
+                      (size_t)kRingWarps * depth * sizeof(uint64_t);
+  DC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the SM's shared-memory carve-out is fixed while CTAs are resident: ask for one under which the filter's CTAs fit beside
+  DC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  kernel<<<dc::sm_count(), kRingWarps * 32, smem, st>>>((const long long*)seg, bytes_per_view, upv, total_views * upv, nbins, depth,
+                                                        flags, counts, (unsigned long long*)outside);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
 // One warp per view: ids present (ascending) minus the smallest -> rows 0,1,2,... A lane looks at one bin of
 // each 32-bin chunk and ballots give the ascending rank of every present id. Present ids are ascending, so every
 // id below n_q is preceded only by ids below n_q: its row is simply its rank minus one (the dropped smallest id).
@@ -190,6 +384,23 @@ extern "C" int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_vi
   cudaStream_t st = dc::as_stream(stream);
   DC_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (size_t)total_views * nbins, st));
   DC_CUDA(cudaMemsetAsync(outside, 0, sizeof(uint64_t) * 4 * (size_t)total_views, st));
+  // int64 maps with 16-byte aligned views, enough of them to give every SM a few MB: the ring kernel (bulk copies)
+  const int64_t bytes_per_view = pixels_per_view * esize;
+  const char* mode = getenv("DC_SEG_MODE");  // "ldg" / "ring": force one kernel (benchmarks/ring_probe.py)
+  const bool want_ring = mode ? strcmp(mode, "ring") == 0 : dc::stream_overlap();
+  const bool ring_ok = want_ring && seg_dtype == DC_I64 && (uintptr_t)seg % 16 == 0 && bytes_per_view % 16 == 0 &&
+                       total_views * bytes_per_view >= (int64_t)dc::sm_count() * (4 << 20);
+  if (ring_ok) {
+    // 12 warps x 3 slots x 2 KB: 7.0 TB/s alone (16 warps: 7.25, 8 warps: 5.4), 21.5 K registers and 74 KB per SM
+    int depth = kRingDepthDefault, warps = 12, carve = dc::stream_overlap() ? dc::kOverlapCarveoutPct : cudaSharedmemCarveoutDefault;
+    if (const char* e = getenv("DC_SEG_STAGES")) depth = max(2, min(12, atoi(e)));
+    if (const char* e = getenv("DC_SEG_WARPS")) warps = atoi(e);
+    if (const char* e = getenv("DC_CARVEOUT_PCT")) carve = atoi(e);
+    const int flags = getenv("DC_SEG_FLAGS") ? atoi(getenv("DC_SEG_FLAGS")) : 0;
+    if (warps == 16) return launch_ring<16, 3>(seg, bytes_per_view, total_views, nbins, depth, flags, carve, counts, outside, st);
+    if (warps == 8) return launch_ring<8, 4>(seg, bytes_per_view, total_views, nbins, depth, flags, carve, counts, outside, st);
+    return launch_ring<12, 3>(seg, bytes_per_view, total_views, nbins, depth, flags, carve, counts, outside, st);
+  }
   // CTAs of ~512 KB: enough of them per view to fill the machine a few times over when there are few views, and small
   // enough that the last wave does not leave SMs idle when there are many (4672 views of 2.4 MB: one CTA per view
   // ran at 6.9 TB/s, four at 7.3 TB/s)

@@ -435,6 +435,10 @@ class _Tick:
         return False
 
 
+def _no_join():
+    return None
+
+
 class FusionEngine:
     """Launch sequences over a SceneBatch. Every method only enqueues work on the current stream."""
 
@@ -447,6 +451,19 @@ class FusionEngine:
         # object-level similarity weights below this are re-evaluated in fp64 (dc_view_weights); inf = every row
         self.refine_below = float(os.environ.get("DC_REFINE_BELOW", "0.02"))
         self.profile: Optional[Dict[str, list]] = None  # name -> [(start_event, end_event)] when enabled
+        # object branch and visibility branch of fuse_object_level on two streams (DC_OVERLAP=0: one stream)
+        self._side: Dict[Optional[int], "torch.cuda.Stream"] = {}
+        self.overlap = os.environ.get("DC_OVERLAP", "1") != "0"
+
+    @property
+    def overlap(self) -> bool:
+        return self._overlap
+
+    @overlap.setter
+    def overlap(self, on: bool):
+        # the library shapes the two kernels that share the SMs accordingly (include/dropclip.h: dc_set_stream_overlap)
+        self._overlap = bool(on)
+        self.lib.dc_set_stream_overlap(int(self._overlap))
 
     def _tick(self, name: str):
         """Context manager recording CUDA events around a launch group on the current stream."""
@@ -669,20 +686,53 @@ class FusionEngine:
 
     # ------------------------------------------------------------------ whole object-level pass
     def fuse_object_level(self, b: SceneBatch, threshold=0.05, use_visibility=False, use_similarity=True,
-                          sim_kernel="max", mask_dtype=torch.uint8, sorted_gather: bool = True):
+                          sim_kernel="max", mask_dtype=torch.uint8, sorted_gather: bool = True, join: bool = True):
         """Device-resident hot path of fuse_obj_prior (utils/feature_fusion.py:272-335) for a batch:
         visibility -> instance tables -> view scores -> weights -> segmented weighted mean.
         With `sorted_gather` the visibility result is returned as bit records (+ rank) to be expanded
-        by compact_visibility / unpack_visibility; otherwise as the full (V,N) mask blocks."""
+        by compact_visibility / unpack_visibility; otherwise as the full (V,N) mask blocks.
+        `join=False`: the object branch is still running on the side stream when this returns; the caller enqueues its
+        own consumers of the visibility result first and then calls out["join"]() before touching fused / weight_obj."""
         out = {}
-        if sorted_gather:
-            out["records"], out["rank"], out["any_visible"] = self.visibility_sorted(b, threshold)
-        else:
-            out["mask"], out["any_visible"], _ = self.visibility(b, threshold, mask_dtype)
-        tables = self.seg_tables(b)
-        fused, weight = self.object_features(b, tables, use_visibility, use_similarity, sim_kernel)
-        out.update({"fused": fused, "weight_obj": weight, "view_status": tables[4]})
+        if not (self.overlap and sorted_gather):
+            if sorted_gather:
+                out["records"], out["rank"], out["any_visible"] = self.visibility_sorted(b, threshold)
+            else:
+                out["mask"], out["any_visible"], _ = self.visibility(b, threshold, mask_dtype)
+            tables = self.seg_tables(b)
+            fused, weight = self.object_features(b, tables, use_visibility, use_similarity, sim_kernel)
+            out.update({"fused": fused, "weight_obj": weight, "view_status": tables[4], "join": _no_join})
+            return out
+        # Two branches that share no data until the caller combines them: instance tables -> scores -> weighted mean
+        # (HBM-bound: the int64 maps) on the side stream, point visibility (issue-bound) on the current stream. The
+        # histogram kernel is shaped to sit beside the filter's CTAs on every SM (csrc/seg_table.cu), so the two
+        # overlap instead of alternating. Side-stream tensors come from that stream's allocator pool; the ones handed
+        # back are recorded on the caller's stream.
+        main = torch.cuda.current_stream(b.device)
+        side = self._side_stream(b.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            tables = self.seg_tables(b)
+            fused, weight = self.object_features(b, tables, use_visibility, use_similarity, sim_kernel)
+        out["records"], out["rank"], out["any_visible"] = self.visibility_sorted(b, threshold)
+        crossing = [fused, weight] + [t for t in tables if t is not None]
+
+        def join_now():
+            main.wait_stream(side)
+            for t in crossing:
+                t.record_stream(main)
+
+        out.update({"fused": fused, "weight_obj": weight, "view_status": tables[4], "join": join_now})
+        if join:
+            join_now()
+            out["join"] = _no_join
         return out
+
+    def _side_stream(self, device):
+        key = torch.device(device).index
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=device)
+        return self._side[key]
 
     # ------------------------------------------------------------------ pixel-level path
     def pixel_fuse(self, b: SceneBatch, mask_u8, sim_kernel, norm_feat: bool, spatial_order: bool = True, normalize: bool = False):

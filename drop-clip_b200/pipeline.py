@@ -369,9 +369,11 @@ class FusionPipeline:
         with torch.cuda.stream(self.s_compute):
             self.s_compute.wait_event(ar.copied_in)
             l0 = eng.launches
-            res = eng.fuse_object_level(b, self.threshold, self.use_visibility, self.use_similarity, self.sim_kernel, torch.uint8)
+            res = eng.fuse_object_level(b, self.threshold, self.use_visibility, self.use_similarity, self.sim_kernel, torch.uint8,
+                                        join=False)
             _, kept_off, _, out_off, cmask, _ = eng.compact_visibility(b, res["any_visible"], res["records"], res["rank"],
                                                                        torch.uint8, host_sizes=False)
+            res["join"]()
             self.launches += eng.launches - l0
             ar.computed.record(self.s_compute)
         tm, tp, tq, tw, tv = int(host["mask"][-1]), int(pp[-1]), int(pq[-1]), int(host["wobj"][-1]), int(pv[-1])

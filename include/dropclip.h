@@ -62,6 +62,12 @@ DC_API int dc_abi_version(void);
 DC_API const char* dc_last_error(void);
 /* host out-params; any may be NULL */
 DC_API int dc_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes);
+/* Two-stream mode of the object-level step (engine.FusionEngine.fuse_object_level): when on (the default), the
+ * instance-histogram pass of the object branch and the visibility filter of the point branch are shaped to share every
+ * SM (dc_seg_histogram takes its bulk-copy ring kernel for large int64 batches, and both kernels ask for the same
+ * shared-memory carve-out, because an SM cannot change it while CTAs are resident). Off: each kernel is configured for
+ * running alone. Results are identical either way. Process-wide; returns the previous setting. */
+DC_API int dc_set_stream_overlap(int on);
 
 /* ------------------------------------------------------------------------------------------
  * (1)+(2) Projection, depth-tolerance visibility and instance-mask lookup.
