@@ -34,10 +34,11 @@ inline cudaStream_t as_stream(dc_stream_t s) { return reinterpret_cast<cudaStrea
 int sm_count();  // cached per process (device 0 of the current context)
 
 // dc_set_stream_overlap(): the histogram ring kernel and the visibility filter share the SMs (two streams). Both then
-// ask for this shared-memory carve-out: 164 KB holds the ring CTA (74 KB) and two filter CTAs (2 x 34 KB at <= 96 views)
-// and leaves the filter's depth gathers ~90 KB of L1 (with the maximum carve-out the filter alone runs 24 % slower).
+// ask for this shared-memory carve-out: 132 KB holds the ring CTA (76 KB) and one filter CTA (34 KB at <= 96 views) and
+// leaves ~120 KB of L1 to the filter's depth gathers (70 % L1 hit rate). Measured on the headline step: 132 KB 2.93-2.99 ms,
+// 164 KB (two filter CTAs beside the ring) 2.95-3.08 ms, 228 KB 3.3-3.6 ms (the filter alone runs 24 % slower without L1).
 bool stream_overlap();
-constexpr int kOverlapCarveoutPct = 72;
+constexpr int kOverlapCarveoutPct = 58;
 
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }

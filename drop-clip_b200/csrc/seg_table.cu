@@ -152,6 +152,22 @@ __device__ __forceinline__ void bulk_load_evict_first(void* smem_dst, const void
       : "memory");
 }
 
+// Waiting for a bulk copy with a suspend-time hint: the warp sleeps in the barrier unit instead of re-issuing try_wait.
+// (This kernel is always waiting for HBM; with the plain spin loop 2/3 of its 1.08 G warp instructions per launch were
+// try_wait re-issues - issue slots taken from the issue-bound filter that shares the SM; ncu: profiles/r02_seg_ring.md.)
+__device__ __forceinline__ void mbar_wait_suspended(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(dc::umma::smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+  } while (!ok);
+}
+
 template <int kRingWarps, int kMinCtas>
 __global__ void __launch_bounds__(kRingWarps * 32, kMinCtas)
 seg_histogram_ring_kernel(const long long* __restrict__ seg, int64_t bytes_per_view, int units_per_view, int64_t total_units,
@@ -227,7 +243,10 @@ seg_histogram_ring_kernel(const long long* __restrict__ seg, int64_t bytes_per_v
     const int b = view_end(v);
     unsigned long long* outside = outside_out + 4 * v;
     for (int j = (v == v_first ? j_first : 0) + w; j < b; j += kRingWarps) {
-      mbar_wait(full + slot, parity);
+      if (flags & 4)
+        mbar_wait(full + slot, parity);
+      else
+        mbar_wait_suspended(full + slot, parity);
       const int n_vec = (j == units_per_view - 1 ? last_bytes : kUnit) >> 4;
       const int4* unit = reinterpret_cast<const int4*>(my_ring + slot * kUnit);
       int4 r[4];
@@ -387,11 +406,11 @@ extern "C" int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_vi
   // int64 maps with 16-byte aligned views, enough of them to give every SM a few MB: the ring kernel (bulk copies)
   const int64_t bytes_per_view = pixels_per_view * esize;
   const char* mode = getenv("DC_SEG_MODE");  // "ldg" / "ring": force one kernel (benchmarks/ring_probe.py)
-  const bool want_ring = mode ? strcmp(mode, "ring") == 0 : dc::stream_overlap();
-  const bool ring_ok = want_ring && seg_dtype == DC_I64 && (uintptr_t)seg % 16 == 0 && bytes_per_view % 16 == 0 &&
-                       total_views * bytes_per_view >= (int64_t)dc::sm_count() * (4 << 20);
+  const bool forced = mode && strcmp(mode, "ring") == 0;
+  const bool want_ring = forced || (!mode && dc::stream_overlap() && total_views * bytes_per_view >= (int64_t)dc::sm_count() * (4 << 20));
+  const bool ring_ok = want_ring && seg_dtype == DC_I64 && (uintptr_t)seg % 16 == 0 && bytes_per_view % 16 == 0;
   if (ring_ok) {
-    // 12 warps x 3 slots x 2 KB: 7.0 TB/s alone (16 warps: 7.25, 8 warps: 5.4), 21.5 K registers and 74 KB per SM
+    // 12 warps x 3 slots x 2 KB: 6.8-7.0 TB/s alone (16 warps: 7.25, 8 warps: 5.4), 21.5 K registers and 74 KB per SM
     int depth = kRingDepthDefault, warps = 12, carve = dc::stream_overlap() ? dc::kOverlapCarveoutPct : cudaSharedmemCarveoutDefault;
     if (const char* e = getenv("DC_SEG_STAGES")) depth = max(2, min(12, atoi(e)));
     if (const char* e = getenv("DC_SEG_WARPS")) warps = atoi(e);

@@ -583,8 +583,29 @@ class FusionEngine:
         return counts, outside, row_object, object_row, status
 
     # ------------------------------------------------------------------ (3)+(4)
-    def object_features(self, b: SceneBatch, tables, use_visibility: bool, use_similarity: bool, sim_kernel):
-        """Returns (fused [sum Q, C] f32, weight_obj [wobj layout] f32)."""
+    def view_scores(self, b: SceneBatch):
+        """Cosine scores of every feature row against its scene's queries (utils/feature_fusion.py:106-124): returns
+        (sims [rows, ld] f32, ld, workspace holding the normalised fp16 planes). Independent of the instance tables, so
+        the two-stream step runs it ahead of the histogram pass."""
+        dim = int(b.feats.shape[1])
+        max_q = max(b.n_queries)
+        ld = self.lib.dc_view_score_ld(max_q)
+        sims = torch.empty((max(b.total_rows, 1), ld), dtype=torch.float32, device=b.device)
+        fdt = _lib.torch_dtype_code(b.feats.dtype)
+        ws_bytes = self.lib.dc_view_score_workspace(b.total_rows, b.total_queries, dim, fdt)
+        ws = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=b.device)
+        shift = (-ws.data_ptr()) % 1024
+        ws = ws[shift:shift + ws_bytes]
+        with self._tick("view_score"):
+            check(self.lib.dc_view_score(ptr(b.feats), fdt, b.total_rows, dim, ptr(b.off["feat"]), ptr(b.off["view"]),
+                                         ptr(b.queries), ptr(b.off["query"]), b.total_queries, b.n_scenes, max_q,
+                                         ptr(sims), ld, ptr(ws), ws_bytes, current_stream()))
+        self.launches += 4
+        return sims, ld, ws
+
+    def object_features(self, b: SceneBatch, tables, use_visibility: bool, use_similarity: bool, sim_kernel, scores=None):
+        """Returns (fused [sum Q, C] f32, weight_obj [wobj layout] f32). `scores`: result of view_scores(b) if the caller
+        has already enqueued it."""
         counts, _, row_object, object_row, _ = tables
         dim = int(b.feats.shape[1])
         max_q = max(b.n_queries)
@@ -593,18 +614,7 @@ class FusionEngine:
         sims, ld = None, 0
         kern = SIM_KERNELS[sim_kernel] if use_similarity else _lib.DC_SIM_NONE
         if use_similarity:
-            ld = self.lib.dc_view_score_ld(max_q)
-            sims = torch.empty((max(b.total_rows, 1), ld), dtype=torch.float32, device=b.device)
-            fdt = _lib.torch_dtype_code(b.feats.dtype)
-            ws_bytes = self.lib.dc_view_score_workspace(b.total_rows, b.total_queries, dim, fdt)
-            ws = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=b.device)
-            shift = (-ws.data_ptr()) % 1024
-            ws = ws[shift:shift + ws_bytes]
-            with self._tick("view_score"):
-                check(self.lib.dc_view_score(ptr(b.feats), fdt, b.total_rows, dim, ptr(b.off["feat"]), ptr(b.off["view"]),
-                                             ptr(b.queries), ptr(b.off["query"]), b.total_queries, b.n_scenes, max_q,
-                                             ptr(sims), ld, ptr(ws), ws_bytes, current_stream()))
-            self.launches += 4
+            sims, ld, ws = scores if scores is not None else self.view_scores(b)
         view_mm = torch.empty(self.lib.dc_view_weights_scratch(b.total_views, b.total_rows) // 4 + 1, dtype=torch.int32,
                               device=b.device) if use_similarity else None
         check(self.lib.dc_view_weights(ptr(sims), ld, ptr(b.off["feat"]), ptr(b.off["view_scene"]), ptr(b.off["view"]),
@@ -712,8 +722,10 @@ class FusionEngine:
         side = self._side_stream(b.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
+            # scores first: they do not need the tables, and the point branch starts with its latency-bound sort passes
+            scores = self.view_scores(b) if use_similarity else None
             tables = self.seg_tables(b)
-            fused, weight = self.object_features(b, tables, use_visibility, use_similarity, sim_kernel)
+            fused, weight = self.object_features(b, tables, use_visibility, use_similarity, sim_kernel, scores)
         out["records"], out["rank"], out["any_visible"] = self.visibility_sorted(b, threshold)
         crossing = [fused, weight] + [t for t in tables if t is not None]
 
@@ -731,7 +743,8 @@ class FusionEngine:
     def _side_stream(self, device):
         key = torch.device(device).index
         if key not in self._side:
-            self._side[key] = torch.cuda.Stream(device=device)
+            # high priority: the object branch ends in a chain of small kernels that should not queue behind filter CTAs
+            self._side[key] = torch.cuda.Stream(device=device, priority=int(os.environ.get("DC_SIDE_PRIORITY", "-1")))
         return self._side[key]
 
     # ------------------------------------------------------------------ pixel-level path
