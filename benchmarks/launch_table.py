@@ -21,7 +21,8 @@ steps = [names[a:b] for a, b in zip(firsts, firsts[1:] + [len(names)])] or [name
 # the last step over the reference's int64 instance maps (bench.py times a uint8-map variant afterwards)
 wide = [st for st in steps if any("seg_histogram_ring" in n or "seg_histogram_kernel<long long>" in n for n, _, _ in st)]
 headline = [st for st in wide if any("unpack_compact_wide" in n for n, _, _ in st)]  # uint8 masks (not the full-output variant)
-last = (headline or wide or steps)[-1]
+ring = [st for st in headline if any("seg_histogram_ring" in n for n, _, _ in st)]  # the two-stream step, if the run has one
+last = (ring or headline or wide or steps)[-1]
 total = sum(v for _, v, _ in last)
 for n, v, g in last:
     short = n.replace("<unnamed>::", "").split("(")[0][:70]

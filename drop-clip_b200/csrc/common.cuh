@@ -34,9 +34,10 @@ inline cudaStream_t as_stream(dc_stream_t s) { return reinterpret_cast<cudaStrea
 int sm_count();  // cached per process (device 0 of the current context)
 
 // dc_set_stream_overlap(): the histogram ring kernel and the visibility filter share the SMs (two streams). Both then
-// ask for this shared-memory carve-out: 132 KB holds the ring CTA (76 KB) and one filter CTA (34 KB at <= 96 views) and
-// leaves ~120 KB of L1 to the filter's depth gathers (70 % L1 hit rate). Measured on the headline step: 132 KB 2.93-2.99 ms,
-// 164 KB (two filter CTAs beside the ring) 2.95-3.08 ms, 228 KB 3.3-3.6 ms (the filter alone runs 24 % slower without L1).
+// ask for this shared-memory carve-out: 132 KB holds the ring CTA (50 KB) and two filter CTAs (34 KB each at <= 96 views)
+// and leaves ~120 KB of L1 to the filter's depth gathers (70 % L1 hit rate). Measured on the headline step
+// (profiles/r02_seg_ring.md): 132 KB 2.75-2.78 ms, 164 KB with a deeper ring 2.80-3.02 ms, 228 KB 3.3-3.6 ms (the filter
+// alone runs 24 % slower without its L1); one stream 3.58 ms.
 bool stream_overlap();
 constexpr int kOverlapCarveoutPct = 58;
 

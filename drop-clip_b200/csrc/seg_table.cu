@@ -10,6 +10,9 @@
 // reads and touches the shared-memory histogram only when the id changes.
 #include <stdlib.h>
 
+#include <algorithm>
+#include <atomic>
+
 #include "common.cuh"
 #include "umma.cuh"  // mbarrier helpers
 
@@ -130,7 +133,8 @@ __global__ void __launch_bounds__(kThreads) seg_histogram_kernel(const T* __rest
 // The histogram pass is HBM-bound and needs few issue slots; the visibility filter that shares the step
 // is issue-bound and needs little HBM. The engine therefore runs the two on different streams, and this
 // kernel is shaped to live BESIDE the filter on every SM instead of alternating with it:
-//   * persistent, one CTA per SM, few warps: two filter CTAs (2 x 256 x 80 registers, 2 x 33 KB) fit next to it;
+//   * persistent, one CTA per SM, 12 warps x 64 registers and ~50 KB of shared memory: two filter CTAs (2 x 256 x 80
+//     registers, 2 x 34 KB) fit next to it, with ~120 KB of the SM left to the L1 the filter's depth gathers live on;
 //   * the bytes in flight that a streaming kernel needs (~50 KB per SM at 7 TB/s) come from shared-memory
 //     rings filled by 1-D bulk copies (cp.async.bulk -> mbarrier complete_tx, L2 evict-first), not from the
 //     registers of hundreds of resident threads;
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(kThreads) seg_histogram_kernel(const T* __rest
 // Counting is the same run-length scheme as above. A lane owns 64 contiguous bytes = eight neighbouring pixels:
 // "all eight equal" is an XOR/OR tree on the ALU, then one 64-bit compare against the current run.
 constexpr int kUnit = 2048;  // bytes per warp unit: 32 lanes x 64 B
-constexpr int kRingDepthDefault = 3;
+constexpr int kRingDepthDefault = 2;
 
 __device__ __forceinline__ void bulk_load_evict_first(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
                                                       uint64_t policy) {
@@ -168,141 +172,169 @@ __device__ __forceinline__ void mbar_wait_suspended(uint64_t* bar, uint32_t pari
   } while (!ok);
 }
 
+// acc | (x ^ ref) as ONE three-input logic instruction (written as C the compiler turns the equality test of eight
+// 64-bit ids into a serial chain of 14 predicate-setting compares: ~180 cycles of dependent latency per unit)
+__device__ __forceinline__ unsigned or_xor(unsigned acc, unsigned x, unsigned ref) {
+  unsigned d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(d) : "r"(x), "r"(ref), "r"(acc));  // (a ^ b) | c
+  return d;
+}
+
+// Views are handed out dynamically (one atomic ticket per view): CTAs that share their SM with more filter CTAs, or that
+// were placed late because their SM was full at launch time, simply take fewer views. (With a static split of the
+// batch the step time jumped between 2.8 and 4.0 ms depending on where the 148 CTAs had landed.)
+constexpr int kTicketSlots = 64;
+__device__ unsigned g_ring_tickets[kTicketSlots];
+
 template <int kRingWarps, int kMinCtas>
 __global__ void __launch_bounds__(kRingWarps * 32, kMinCtas)
-seg_histogram_ring_kernel(const long long* __restrict__ seg, int64_t bytes_per_view, int units_per_view, int64_t total_units,
-                          int nbins, int depth, int flags, uint32_t* __restrict__ counts,
+seg_histogram_ring_kernel(const long long* __restrict__ seg, int64_t bytes_per_view, int units_per_view, int total_views,
+                          int nbins, int depth, int flags, unsigned* __restrict__ ticket, uint32_t* __restrict__ counts,
                           unsigned long long* __restrict__ outside_out) {
   using namespace dc::umma;
   constexpr int kRingThreads = kRingWarps * 32;
-  extern __shared__ __align__(128) unsigned char s_ring[];  // [warps][depth][2 KB], histogram, full[warps][depth]
+  extern __shared__ __align__(128) unsigned char s_ring[];  // [warps][depth][2 KB], histogram, full[warps][depth], views[2]
   const size_t ring_bytes = (size_t)kRingWarps * depth * kUnit;
   unsigned* s_hist = reinterpret_cast<unsigned*>(s_ring + ring_bytes);
   uint64_t* full_all = reinterpret_cast<uint64_t*>(s_ring + ring_bytes + ((nbins * 4 + 15) & ~15));
-  const int64_t g0 = total_units * blockIdx.x / gridDim.x, g1 = total_units * (blockIdx.x + 1) / gridDim.x;
-  if (g1 <= g0) return;
+  volatile int* s_view = reinterpret_cast<volatile int*>(full_all + kRingWarps * depth);  // the CTA's n-th view: s_view[n & 1]
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingWarps * depth; ++i) mbar_init(full_all + i, 1);
     fence_barrier_init();
+    s_view[0] = (int)atomicAdd(ticket, 1u);
+    s_view[1] = (int)atomicAdd(ticket, 1u);
   }
   for (int i = threadIdx.x; i < nbins; i += kRingThreads) s_hist[i] = 0;
   __syncthreads();
 
-  const int64_t v_first = g0 / units_per_view, v_last = (g1 - 1) / units_per_view;
-  const int j_first = (int)(g0 - v_first * units_per_view);
   const int last_bytes = (int)(bytes_per_view - (int64_t)(units_per_view - 1) * kUnit);  // of a view's last unit
-  auto view_end = [&](int64_t v) -> int {  // end of this CTA's unit range inside view v
-    const int64_t e = g1 - v * units_per_view;
-    return e < units_per_view ? (int)e : units_per_view;
-  };
-  unsigned char* my_ring = s_ring + (size_t)w * depth * kUnit;
-  uint64_t* full = full_all + w * depth;
-  const char* base = reinterpret_cast<const char*>(seg);
+  unsigned char* const my_ring = s_ring + (size_t)w * depth * kUnit;
+  uint64_t* const full = full_all + w * depth;
+  const char* const base = reinterpret_cast<const char*>(seg);
+  // units w, w + warps, ... of every view are this warp's (the launcher guarantees units_per_view >= 4 * warps * depth,
+  // so a warp's producer lane never runs two views ahead of its consumer)
+  const int n_it = (units_per_view - w + kRingWarps - 1) / kRingWarps;
+  const bool ends_partial = last_bytes != kUnit && w + (n_it - 1) * kRingWarps == units_per_view - 1;
 
-  // producer state (lane 0): the warp's next unit to load = (pv, pj), into slot pslot
+  // ---- producer state (lane 0): the warp's next unit to load is unit pj of the CTA's pn-th view, at psrc, into slot pslot
   uint64_t policy = 0;
-  int64_t pv = v_first;
-  int pb = view_end(pv), pj = j_first + w, pslot = 0;
-  auto skip_empty_views = [&]() {
-    while (pj >= pb && pv < v_last) {
-      ++pv;
-      pb = view_end(pv);
-      pj = w;
-    }
+  int pn = 0, pj = w, pslot = 0;
+  bool p_has = false;
+  const char* psrc = nullptr;
+  auto open_view = [&]() {
+    const int pv = s_view[pn & 1];
+    p_has = pv < total_views;
+    psrc = base + (int64_t)pv * bytes_per_view + (int64_t)w * kUnit;
+    pj = w;
   };
   auto issue = [&]() {
     const uint32_t bytes = (uint32_t)(pj == units_per_view - 1 ? last_bytes : kUnit);
-    const char* src = base + pv * bytes_per_view + (int64_t)pj * kUnit;
     mbar_expect_tx(full + pslot, bytes);
     if (flags & 2)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(smem_u32(my_ring + pslot * kUnit)), "l"(src), "r"(bytes), "r"(smem_u32(full + pslot)) : "memory");
+                   ::"r"(smem_u32(my_ring + pslot * kUnit)), "l"(psrc), "r"(bytes), "r"(smem_u32(full + pslot)) : "memory");
     else
-      bulk_load_evict_first(my_ring + pslot * kUnit, src, bytes, full + pslot, policy);
+      bulk_load_evict_first(my_ring + pslot * kUnit, psrc, bytes, full + pslot, policy);
     pslot = (pslot == depth - 1) ? 0 : pslot + 1;
     pj += kRingWarps;
-    skip_empty_views();
+    psrc += kRingWarps * kUnit;
+    if (pj >= units_per_view) {  // on to the CTA's next view (claimed one view ahead, see the flush below)
+      ++pn;
+      open_view();
+    }
   };
   if (lane == 0) {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    skip_empty_views();
-    for (int d = 0; d < depth && pj < pb; ++d) issue();
+    open_view();
+    for (int d = 0; d < depth && p_has; ++d) issue();
   }
 
+  // ---- consumer: a lane owns 64 contiguous bytes of every unit; its four 16-byte reads are rotated by lane so that
+  // the eight lanes of a shared-memory phase fall into eight different 16-byte bank groups
+  int off[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    off[k] = 16 * (4 * lane + ((k + (lane >> 1)) & 3));
+    asm volatile("" : "+r"(off[k]));  // keep the four offsets in registers (otherwise recomputed from the lane id per unit)
+  }
   RunAcc run{-1, 0};
   int slot = 0;
   uint32_t parity = 0;
-  // a lane's four 16-byte reads of its 64 bytes are rotated by lane so that the eight lanes of a shared-memory phase
-  // fall into eight different 16-byte bank groups
-  int idx[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) idx[k] = 4 * lane + ((k + (lane >> 1)) & 3);
+  const unsigned char* slot_ptr = my_ring;
 
-  for (int64_t v = v_first; v <= v_last; ++v) {
-    const int b = view_end(v);
-    unsigned long long* outside = outside_out + 4 * v;
-    for (int j = (v == v_first ? j_first : 0) + w; j < b; j += kRingWarps) {
+  for (int n = 0;; ++n) {
+    const int v = s_view[n & 1];
+    if (v >= total_views) break;
+    unsigned long long* outside = outside_out + 4 * (int64_t)v;
+    for (int it = 0; it < n_it; ++it) {
       if (flags & 4)
         mbar_wait(full + slot, parity);
       else
         mbar_wait_suspended(full + slot, parity);
-      const int n_vec = (j == units_per_view - 1 ? last_bytes : kUnit) >> 4;
-      const int4* unit = reinterpret_cast<const int4*>(my_ring + slot * kUnit);
-      int4 r[4];
+      if (!(ends_partial && it == n_it - 1)) {
+        int4 r[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) r[k] = unit[idx[k] < n_vec ? idx[k] : 0];
-      if (flags & 1) {
-        run.cnt += (unsigned)(r[0].x ^ r[1].y ^ r[2].z ^ r[3].w) & 1u;
-      } else if (n_vec == kUnit / 16) {
-        const unsigned lo0 = (unsigned)r[0].x, hi0 = (unsigned)r[0].y;
-        unsigned d = ((unsigned)r[0].z ^ lo0) | ((unsigned)r[0].w ^ hi0);
-#pragma unroll
-        for (int k = 1; k < 4; ++k)
-          d |= ((unsigned)r[k].x ^ lo0) | ((unsigned)r[k].y ^ hi0) | ((unsigned)r[k].z ^ lo0) | ((unsigned)r[k].w ^ hi0);
-        if (d == 0) {  // eight equal ids
-          const long long id = (long long)(((unsigned long long)hi0 << 32) | lo0);
-          if (id != run.cur) {
-            flush_run(run, s_hist, outside, nbins);
-            run.cur = id;
-            run.cnt = 0;
-          }
-          run.cnt += 8;
+        for (int k = 0; k < 4; ++k) r[k] = *reinterpret_cast<const int4*>(slot_ptr + off[k]);
+        if (flags & 1) {
+          run.cnt += (unsigned)(r[0].x ^ r[1].y ^ r[2].z ^ r[3].w) & 1u;
         } else {
-          // an object boundary inside the lane's eight pixels. The other lanes of the warp wait for this path, so it is
-          // kept short and free of dependent chains: close the run, then one shared-memory atomic per pixel.
-          flush_run(run, s_hist, outside, nbins);
-          run.cur = -1;
-          run.cnt = 0;
-          const unsigned hi_any = (unsigned)r[0].y | (unsigned)r[0].w | (unsigned)r[1].y | (unsigned)r[1].w | (unsigned)r[2].y |
-                                  (unsigned)r[2].w | (unsigned)r[3].y | (unsigned)r[3].w;
-          const unsigned lo_max = max(max(max((unsigned)r[0].x, (unsigned)r[0].z), max((unsigned)r[1].x, (unsigned)r[1].z)),
-                                      max(max((unsigned)r[2].x, (unsigned)r[2].z), max((unsigned)r[3].x, (unsigned)r[3].z)));
-          if (hi_any == 0 && lo_max < (unsigned)nbins) {
+          const unsigned lo0 = (unsigned)r[0].x, hi0 = (unsigned)r[0].y;
+          unsigned dl = (unsigned)r[0].z ^ lo0, dh = (unsigned)r[0].w ^ hi0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              atomicAdd(s_hist + (unsigned)r[k].x, 1u);
-              atomicAdd(s_hist + (unsigned)r[k].z, 1u);
+          for (int k = 1; k < 4; ++k) {
+            dl = or_xor(or_xor(dl, (unsigned)r[k].x, lo0), (unsigned)r[k].z, lo0);
+            dh = or_xor(or_xor(dh, (unsigned)r[k].y, hi0), (unsigned)r[k].w, hi0);
+          }
+          if ((dl | dh) == 0) {  // eight equal ids
+            const long long id = (long long)(((unsigned long long)hi0 << 32) | lo0);
+            if (id != run.cur) {
+              flush_run(run, s_hist, outside, nbins);
+              run.cur = id;
+              run.cnt = 0;
             }
-          } else {  // ids outside the histogram (negative background, id >= nbins): the general path
+            run.cnt += 8;
+          } else {
+            // an object boundary inside the lane's eight pixels. The other lanes of the warp wait for this path, so it
+            // is kept short and free of dependent chains: close the run, then one shared-memory atomic per pixel.
+            flush_run(run, s_hist, outside, nbins);
+            run.cur = -1;
+            run.cnt = 0;
+            const unsigned hi_any = (unsigned)r[0].y | (unsigned)r[0].w | (unsigned)r[1].y | (unsigned)r[1].w | (unsigned)r[2].y |
+                                    (unsigned)r[2].w | (unsigned)r[3].y | (unsigned)r[3].w;
+            const unsigned lo_max = max(max(max((unsigned)r[0].x, (unsigned)r[0].z), max((unsigned)r[1].x, (unsigned)r[1].z)),
+                                        max(max((unsigned)r[2].x, (unsigned)r[2].z), max((unsigned)r[3].x, (unsigned)r[3].z)));
+            if (hi_any == 0 && lo_max < (unsigned)nbins) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) consume_vector<long long>(r[k], run, s_hist, outside, nbins);
+              for (int k = 0; k < 4; ++k) {
+                atomicAdd(s_hist + (unsigned)r[k].x, 1u);
+                atomicAdd(s_hist + (unsigned)r[k].z, 1u);
+              }
+            } else {  // ids outside the histogram (negative background, id >= nbins): the general path
+#pragma unroll
+              for (int k = 0; k < 4; ++k) consume_vector<long long>(r[k], run, s_hist, outside, nbins);
+            }
           }
         }
-      } else {
+      } else {  // partial last unit of the view
+        const int n_vec = last_bytes >> 4;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (idx[k] < n_vec) consume_vector<long long>(r[k], run, s_hist, outside, nbins);
+          if ((off[k] >> 4) < n_vec)
+            consume_vector<long long>(*reinterpret_cast<const int4*>(slot_ptr + off[k]), run, s_hist, outside, nbins);
       }
       // every lane has used its registers, so the shared-memory reads of the slot are complete: refill it
       __syncwarp();
-      if (lane == 0 && pj < pb) issue();
+      if (lane == 0 && p_has) issue();
+      slot_ptr += kUnit;
       if (++slot == depth) {
         slot = 0;
+        slot_ptr = my_ring;
         parity ^= 1u;
       }
     }
-    // end of the view (or of the CTA's range): all warps flush into the view's global row
+    // end of the view: all warps flush into the view's global row, and the CTA claims the view after the next one
+    // (slot n & 1 of s_view is free: every warp has read it, and the producer lanes are already in view n + 1)
     flush_run(run, s_hist, outside, nbins);
     run.cur = -1;
     run.cnt = 0;
@@ -310,12 +342,17 @@ seg_histogram_ring_kernel(const long long* __restrict__ seg, int64_t bytes_per_v
     for (int bin = threadIdx.x; bin < nbins; bin += kRingThreads) {
       const unsigned t = s_hist[bin];
       if (t) {
-        atomicAdd(counts + v * nbins + bin, t);
+        atomicAdd(counts + (int64_t)v * nbins + bin, t);
         s_hist[bin] = 0;
       }
     }
+    if (threadIdx.x == 0) s_view[n & 1] = (int)atomicAdd(ticket, 1u);
     __syncthreads();
   }
+}
+
+inline bool ring_fits(int64_t bytes_per_view, int warps, int depth) {
+  return dc::ceil_div<int64_t>(bytes_per_view, kUnit) >= (int64_t)4 * warps * depth;
 }
 
 template <int kRingWarps, int kMinCtas>
@@ -324,12 +361,19 @@ int launch_ring(const void* seg, int64_t bytes_per_view, int64_t total_views, in
   auto kernel = seg_histogram_ring_kernel<kRingWarps, kMinCtas>;
   const int upv = (int)dc::ceil_div<int64_t>(bytes_per_view, kUnit);
   const size_t smem = (size_t)kRingWarps * depth * kUnit + ((sizeof(unsigned) * nbins + 15) & ~(size_t)15) +
-                      (size_t)kRingWarps * depth * sizeof(uint64_t);
+                      (size_t)kRingWarps * depth * sizeof(uint64_t) + 16;
+  // a zeroed ticket counter per launch; launches in flight at the same time use different slots
+  static std::atomic<unsigned> next_slot{0};
+  unsigned* tickets = nullptr;
+  DC_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_ring_tickets));
+  unsigned* ticket = tickets + next_slot.fetch_add(1) % kTicketSlots;
+  DC_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   DC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // the SM's shared-memory carve-out is fixed while CTAs are resident: ask for one under which the filter's CTAs fit beside
   DC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-  kernel<<<dc::sm_count(), kRingWarps * 32, smem, st>>>((const long long*)seg, bytes_per_view, upv, total_views * upv, nbins, depth,
-                                                        flags, counts, (unsigned long long*)outside);
+  const int grid = (int)std::min<int64_t>(dc::sm_count(), total_views);
+  kernel<<<grid, kRingWarps * 32, smem, st>>>((const long long*)seg, bytes_per_view, upv, (int)total_views, nbins, depth, flags, ticket,
+                                              counts, (unsigned long long*)outside);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
@@ -408,12 +452,15 @@ extern "C" int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_vi
   const char* mode = getenv("DC_SEG_MODE");  // "ldg" / "ring": force one kernel (benchmarks/ring_probe.py)
   const bool forced = mode && strcmp(mode, "ring") == 0;
   const bool want_ring = forced || (!mode && dc::stream_overlap() && total_views * bytes_per_view >= (int64_t)dc::sm_count() * (4 << 20));
-  const bool ring_ok = want_ring && seg_dtype == DC_I64 && (uintptr_t)seg % 16 == 0 && bytes_per_view % 16 == 0;
+  int depth = kRingDepthDefault, warps = 12;
+  if (const char* e = getenv("DC_SEG_STAGES")) depth = max(2, min(12, atoi(e)));
+  if (const char* e = getenv("DC_SEG_WARPS")) warps = atoi(e) == 16 ? 16 : atoi(e) == 8 ? 8 : 12;
+  const bool ring_ok = want_ring && seg_dtype == DC_I64 && (uintptr_t)seg % 16 == 0 && bytes_per_view % 16 == 0 &&
+                       ring_fits(bytes_per_view, warps, depth);
   if (ring_ok) {
-    // 12 warps x 3 slots x 2 KB: 6.8-7.0 TB/s alone (16 warps: 7.25, 8 warps: 5.4), 21.5 K registers and 74 KB per SM
-    int depth = kRingDepthDefault, warps = 12, carve = dc::stream_overlap() ? dc::kOverlapCarveoutPct : cudaSharedmemCarveoutDefault;
-    if (const char* e = getenv("DC_SEG_STAGES")) depth = max(2, min(12, atoi(e)));
-    if (const char* e = getenv("DC_SEG_WARPS")) warps = atoi(e);
+    // 12 warps x 2 slots x 2 KB = 48 KB of ring: beside it two filter CTAs fit into the 132 KB carve-out (common.cuh).
+    // Alone: 6.6 TB/s (3 slots: 7.1, 8 warps: 5.8); the two-stream step: 2.75-2.78 ms with 2 slots, 2.80-3.03 with 3.
+    int carve = dc::stream_overlap() ? dc::kOverlapCarveoutPct : cudaSharedmemCarveoutDefault;
     if (const char* e = getenv("DC_CARVEOUT_PCT")) carve = atoi(e);
     const int flags = getenv("DC_SEG_FLAGS") ? atoi(getenv("DC_SEG_FLAGS")) : 0;
     if (warps == 16) return launch_ring<16, 3>(seg, bytes_per_view, total_views, nbins, depth, flags, carve, counts, outside, st);

@@ -388,10 +388,11 @@ def test_seg_histogram_all_dtypes(dtype):
             assert int(outside[v, 2]) == neg.min() and int(outside[v, 3]) - 2 ** 63 == neg.max()
 
 
-@pytest.mark.parametrize("V,HW,nb", [(5, 97 * 131 + 1, 40), (3, 2 * 1024, 256), (1, 6, 8), (700, 480 * 64, 256)])
+@pytest.mark.parametrize("V,HW,nb", [(5, 97 * 263 + 1, 40), (3, 128 * 1024, 256), (1, 24576 + 6, 8), (700, 480 * 64, 256)])
 def test_seg_histogram_ring_kernel(V, HW, nb, monkeypatch):
     """The bulk-copy ring kernel of the two-stream step (csrc/seg_table.cu) against the C oracle and the register-staged
-    kernel: views that end in a partial 2 KB unit, fewer units than CTAs, views split between CTAs, ids outside the bins."""
+    kernel: views that end in a partial 2 KB unit (the ring kernel takes views of at least 96 units = 24 576 pixels),
+    fewer views than CTAs, several views per CTA, ids outside the bins."""
     from dropclip_b200 import _lib
     from oracle import c_oracle
     lib = _lib.load()
