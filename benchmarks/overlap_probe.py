@@ -56,8 +56,11 @@ for overlap, mode, stages, carve, warps in configs:
     eng.profile = {}
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
+    import time
+    h0 = time.perf_counter()
     for _ in range(10):
         keep = step()
+    host_ms = (time.perf_counter() - h0) * 100
     b.record()
     torch.cuda.synchronize()
     prof = eng.profile_ms()
@@ -67,5 +70,5 @@ for overlap, mode, stages, carve, warps in configs:
     if base is None:
         base = sig
     assert sig == base, (sig, base)
-    print(f"overlap={overlap} seg={mode}{stages or ''} warps={warps} carve={carve}: {a.elapsed_time(b) / 10:.3f} ms/step  "
+    print(f"overlap={overlap} seg={mode}{stages or ''} warps={warps} carve={carve}: {a.elapsed_time(b) / 10:.3f} ms/step (host enqueue {host_ms:.2f} ms/step)  "
           + "  ".join(f"{k}={v:.3f}" for k, v in prof.items()), flush=True)

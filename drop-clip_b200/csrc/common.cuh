@@ -34,12 +34,34 @@ inline cudaStream_t as_stream(dc_stream_t s) { return reinterpret_cast<cudaStrea
 int sm_count();  // cached per process (device 0 of the current context)
 
 // dc_set_stream_overlap(): the histogram ring kernel and the visibility filter share the SMs (two streams). Both then
-// ask for this shared-memory carve-out: 132 KB holds the ring CTA (50 KB) and two filter CTAs (34 KB each at <= 96 views)
-// and leaves ~120 KB of L1 to the filter's depth gathers (70 % L1 hit rate). Measured on the headline step
-// (profiles/r02_seg_ring.md): 132 KB 2.75-2.78 ms, 164 KB with a deeper ring 2.80-3.02 ms, 228 KB 3.3-3.6 ms (the filter
-// alone runs 24 % slower without its L1); one stream 3.58 ms.
+// ask for the same shared-memory carve-out - an SM cannot change it while CTAs are resident. 58 % of 228 KB is rounded up
+// by the driver to the 164 KB configuration (ncu: launch__shared_mem_config_size 167.9 KB): room for the ring CTA (50 KB)
+// and two filter CTAs (34 KB each at <= 96 views; registers allow no third), and ~90 KB of L1 left for the filter's depth
+// gathers (70 % L1 hit rate). Measured on the headline step (profiles/r02_seg_ring.md): this setting 2.75-2.78 ms, the
+// 196 KB configuration with 3-slot rings 2.80-2.82 ms, 228 KB 3.3-3.6 ms (the filter alone runs 24 % slower without its
+// L1); one stream 3.58 ms.
 bool stream_overlap();
 constexpr int kOverlapCarveoutPct = 58;
+
+// cudaFuncSetAttribute only when the value differs from the one last set for this kernel on the current device
+// (the attribute calls of a step add up on the host: the two-stream step is enqueued in ~1 ms)
+struct FuncAttrCache {
+  static constexpr int kMaxDevices = 32;
+  int value[kMaxDevices];
+  FuncAttrCache() {
+    for (int i = 0; i < kMaxDevices; ++i) value[i] = -12345;
+  }
+  template <typename K>
+  cudaError_t set(K kernel, cudaFuncAttribute attr, int v) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < kMaxDevices && value[dev] == v) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, attr, v);
+    if (e == cudaSuccess && dev >= 0 && dev < kMaxDevices) value[dev] = v;
+    return e;
+  }
+};
 
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }

@@ -134,15 +134,14 @@ __global__ void __launch_bounds__(kThreads) seg_histogram_kernel(const T* __rest
 // is issue-bound and needs little HBM. The engine therefore runs the two on different streams, and this
 // kernel is shaped to live BESIDE the filter on every SM instead of alternating with it:
 //   * persistent, one CTA per SM, 12 warps x 64 registers and ~50 KB of shared memory: two filter CTAs (2 x 256 x 80
-//     registers, 2 x 34 KB) fit next to it, with ~120 KB of the SM left to the L1 the filter's depth gathers live on;
+//     registers, 2 x 34 KB) fit next to it, with ~90 KB of the SM left to the L1 the filter's depth gathers live on;
 //   * the bytes in flight that a streaming kernel needs (~50 KB per SM at 7 TB/s) come from shared-memory
 //     rings filled by 1-D bulk copies (cp.async.bulk -> mbarrier complete_tx, L2 evict-first), not from the
 //     registers of hundreds of resident threads;
 //   * every warp runs its own ring (2 KB units, `depth` slots, its lane 0 is the producer), so a warp that
 //     meets an object boundary (the slow, per-pixel path) does not hold up the other warps;
-//   * the CTA owns a contiguous range of units of the whole batch, interleaved over its warps, and flushes its
-//     shared-memory histogram whenever the range crosses into the next view (global atomics: a view may be split
-//     between two CTAs).
+//   * a CTA takes whole views by atomic ticket (one view ahead, so the producers never drain at a view boundary),
+//     deals the view's units to its warps round-robin and flushes its shared-memory histogram at the end of the view.
 // Counting is the same run-length scheme as above. A lane owns 64 contiguous bytes = eight neighbouring pixels:
 // "all eight equal" is an XOR/OR tree on the ALU, then one 64-bit compare against the current run.
 constexpr int kUnit = 2048;  // bytes per warp unit: 32 lanes x 64 B
@@ -364,13 +363,20 @@ int launch_ring(const void* seg, int64_t bytes_per_view, int64_t total_views, in
                       (size_t)kRingWarps * depth * sizeof(uint64_t) + 16;
   // a zeroed ticket counter per launch; launches in flight at the same time use different slots
   static std::atomic<unsigned> next_slot{0};
-  unsigned* tickets = nullptr;
-  DC_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_ring_tickets));
+  static unsigned* tickets_of_device[dc::FuncAttrCache::kMaxDevices] = {nullptr};
+  int dev = 0;
+  DC_CUDA(cudaGetDevice(&dev));
+  unsigned* tickets = (dev >= 0 && dev < dc::FuncAttrCache::kMaxDevices) ? tickets_of_device[dev] : nullptr;
+  if (!tickets) {
+    DC_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_ring_tickets));
+    if (dev >= 0 && dev < dc::FuncAttrCache::kMaxDevices) tickets_of_device[dev] = tickets;
+  }
   unsigned* ticket = tickets + next_slot.fetch_add(1) % kTicketSlots;
   DC_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
-  DC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static dc::FuncAttrCache smem_attr, carve_attr;
+  DC_CUDA(smem_attr.set(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // the SM's shared-memory carve-out is fixed while CTAs are resident: ask for one under which the filter's CTAs fit beside
-  DC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  DC_CUDA(carve_attr.set(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   const int grid = (int)std::min<int64_t>(dc::sm_count(), total_views);
   kernel<<<grid, kRingWarps * 32, smem, st>>>((const long long*)seg, bytes_per_view, upv, (int)total_views, nbins, depth, flags, ticket,
                                               counts, (unsigned long long*)outside);
@@ -458,8 +464,8 @@ extern "C" int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_vi
   const bool ring_ok = want_ring && seg_dtype == DC_I64 && (uintptr_t)seg % 16 == 0 && bytes_per_view % 16 == 0 &&
                        ring_fits(bytes_per_view, warps, depth);
   if (ring_ok) {
-    // 12 warps x 2 slots x 2 KB = 48 KB of ring: beside it two filter CTAs fit into the 132 KB carve-out (common.cuh).
-    // Alone: 6.6 TB/s (3 slots: 7.1, 8 warps: 5.8); the two-stream step: 2.75-2.78 ms with 2 slots, 2.80-3.03 with 3.
+    // 12 warps x 2 slots x 2 KB = 48 KB of ring, beside two filter CTAs in the shared carve-out (common.cuh).
+    // Alone: 6.7 TB/s (3 slots: 7.2, 8 warps: 5.8); the two-stream step: 2.75-2.78 ms with 2 slots, 2.80-2.85 with 3.
     int carve = dc::stream_overlap() ? dc::kOverlapCarveoutPct : cudaSharedmemCarveoutDefault;
     if (const char* e = getenv("DC_CARVEOUT_PCT")) carve = atoi(e);
     const int flags = getenv("DC_SEG_FLAGS") ? atoi(getenv("DC_SEG_FLAGS")) : 0;
@@ -477,6 +483,13 @@ extern "C" int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_vi
   unsigned gx = (unsigned)max((int64_t)1, min(want, max((int64_t)1, cap)));
   dim3 grid(gx, (unsigned)total_views);
   const size_t smem = sizeof(unsigned) * nbins;
+  {  // same carve-out as the visibility filter these CTAs may share their SM with (two-stream step)
+    const int carve = dc::stream_overlap() ? dc::kOverlapCarveoutPct : cudaSharedmemCarveoutDefault;
+    static dc::FuncAttrCache c8, c32, c64;
+    if (seg_dtype == DC_U8) DC_CUDA(c8.set(seg_histogram_kernel<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    else if (seg_dtype == DC_I32) DC_CUDA(c32.set(seg_histogram_kernel<int32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    else DC_CUDA(c64.set(seg_histogram_kernel<long long>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  }
   if (seg_dtype == DC_U8)
     seg_histogram_kernel<uint8_t><<<grid, kThreads, smem, st>>>((const uint8_t*)seg, pixels_per_view, nbins, counts, (unsigned long long*)outside);
   else if (seg_dtype == DC_I32)

@@ -453,6 +453,8 @@ class FusionEngine:
         self.profile: Optional[Dict[str, list]] = None  # name -> [(start_event, end_event)] when enabled
         # object branch and visibility branch of fuse_object_level on two streams (DC_OVERLAP=0: one stream)
         self._side: Dict[Optional[int], "torch.cuda.Stream"] = {}
+        self._events: Dict[Optional[int], tuple] = {}
+        self._out_stream: Optional["torch.cuda.Stream"] = None
         self.overlap = os.environ.get("DC_OVERLAP", "1") != "0"
 
     @property
@@ -464,6 +466,18 @@ class FusionEngine:
         # the library shapes the two kernels that share the SMs accordingly (include/dropclip.h: dc_set_stream_overlap)
         self._overlap = bool(on)
         self.lib.dc_set_stream_overlap(int(self._overlap))
+
+    def _alloc_out(self, shape, dtype, device) -> torch.Tensor:
+        """Result tensors of the object branch. While that branch is being enqueued on the side stream
+        (fuse_object_level) they still come from the CALLER's stream pool: they outlive the join, so the caller's
+        allocator may recycle them in its own stream order with no cross-stream bookkeeping (record_stream would park
+        every freed block behind an event, the pools would grow while the host runs ahead, and the resulting
+        cudaMallocs inside the step loop contend between the ranks of a node: 2.78 -> 3.4-3.8 ms per step at N=2).
+        Branch-local scratch stays in the side stream's pool."""
+        if self._out_stream is None:
+            return torch.empty(shape, dtype=dtype, device=device)
+        with torch.cuda.stream(self._out_stream):
+            return torch.empty(shape, dtype=dtype, device=device)
 
     def _tick(self, name: str):
         """Context manager recording CUDA events around a launch group on the current stream."""
@@ -566,15 +580,15 @@ class FusionEngine:
         """Instance histograms and the feature-row <-> object binding of every view."""
         tv = b.total_views
         nbins = hist_bins(max(b.n_queries, default=0))
-        counts = torch.empty((tv, nbins), dtype=torch.int32, device=b.device)
-        outside = torch.empty((max(tv, 1), 4), dtype=torch.int64, device=b.device)
+        counts = self._alloc_out((tv, nbins), torch.int32, b.device)
+        outside = self._alloc_out((max(tv, 1), 4), torch.int64, b.device)
         with self._tick("seg_histogram"):
             check(self.lib.dc_seg_histogram(ptr(b.segs), _lib.torch_dtype_code(b.segs.dtype), tv, b.height * b.width,
                                             nbins, ptr(counts), ptr(outside), current_stream()))
-        row_object = torch.empty(max(b.total_rows, 1), dtype=torch.int32, device=b.device)
+        row_object = self._alloc_out(max(b.total_rows, 1), torch.int32, b.device)
         total_wobj = int(b.off_host["wobj"][-1])
-        object_row = torch.empty(max(total_wobj, 1), dtype=torch.int32, device=b.device)
-        status = torch.empty(max(tv, 1), dtype=torch.int32, device=b.device)
+        object_row = self._alloc_out(max(total_wobj, 1), torch.int32, b.device)
+        status = self._alloc_out(max(tv, 1), torch.int32, b.device)
         check(self.lib.dc_view_table(ptr(counts), ptr(outside), ptr(b.off["feat"]), ptr(b.off["view_scene"]),
                                      ptr(b.off["view"]), ptr(b.off["query"]), ptr(b.off["wobj"]), tv, b.total_rows,
                                      total_wobj, nbins, ptr(row_object), ptr(object_row), ptr(status),
@@ -610,7 +624,8 @@ class FusionEngine:
         dim = int(b.feats.shape[1])
         max_q = max(b.n_queries)
         total_wobj = int(b.off_host["wobj"][-1])
-        weight = torch.zeros(max(total_wobj, 1), dtype=torch.float32, device=b.device)
+        weight = self._alloc_out(max(total_wobj, 1), torch.float32, b.device)
+        weight.zero_()  # on the branch's own stream
         sims, ld = None, 0
         kern = SIM_KERNELS[sim_kernel] if use_similarity else _lib.DC_SIM_NONE
         if use_similarity:
@@ -624,7 +639,7 @@ class FusionEngine:
                                        ptr(b.queries) if use_similarity else None, b.total_rows, ptr(view_mm),
                                        ptr(ws) if (use_similarity and b.feats.dtype == torch.float16) else None,
                                        float(self.refine_below), current_stream()))
-        fused = torch.empty((b.total_queries, dim), dtype=torch.float32, device=b.device)
+        fused = self._alloc_out((b.total_queries, dim), torch.float32, b.device)
         with self._tick("segmented_wmean"):
             check(self.lib.dc_segmented_wmean(ptr(b.feats), _lib.torch_dtype_code(b.feats.dtype), dim, ptr(object_row),
                                               ptr(weight), ptr(b.off["view"]), ptr(b.off["query"]), ptr(b.off["wobj"]),
@@ -716,25 +731,32 @@ class FusionEngine:
         # Two branches that share no data until the caller combines them: instance tables -> scores -> weighted mean
         # (HBM-bound: the int64 maps) on the side stream, point visibility (issue-bound) on the current stream. The
         # histogram kernel is shaped to sit beside the filter's CTAs on every SM (csrc/seg_table.cu), so the two
-        # overlap instead of alternating. Side-stream tensors come from that stream's allocator pool; the ones handed
-        # back are recorded on the caller's stream.
+        # overlap instead of alternating. Branch-local scratch comes from the side stream's allocator pool; everything
+        # handed back is allocated from the caller's pool (_alloc_out).
         main = torch.cuda.current_stream(b.device)
         side = self._side_stream(b.device)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            # scores first: they do not need the tables, and the point branch starts with its latency-bound sort passes
-            scores = self.view_scores(b) if use_similarity else None
-            tables = self.seg_tables(b)
-            fused, weight = self.object_features(b, tables, use_visibility, use_similarity, sim_kernel, scores)
+        fork_evt, join_evt = self._events[torch.device(b.device).index]  # reused every call (no event churn on the host)
+        fork_evt.record(main)
+        side.wait_event(fork_evt)
+        self._out_stream = main
+        try:
+            with torch.cuda.stream(side):
+                # scores first: they do not need the tables, and the point branch starts with its latency-bound sort passes
+                scores = self.view_scores(b) if use_similarity else None
+                tables = self.seg_tables(b)
+                fused, weight = self.object_features(b, tables, use_visibility, use_similarity, sim_kernel, scores)
+                del scores
+        finally:
+            self._out_stream = None
+        join_evt.record(side)
         out["records"], out["rank"], out["any_visible"] = self.visibility_sorted(b, threshold)
-        crossing = [fused, weight] + [t for t in tables if t is not None]
 
         def join_now():
-            main.wait_stream(side)
-            for t in crossing:
-                t.record_stream(main)
+            main.wait_event(join_evt)
 
-        out.update({"fused": fused, "weight_obj": weight, "view_status": tables[4], "join": join_now})
+        # the tables stay referenced by the result until the caller drops it (after the join): their blocks belong to the
+        # caller's stream pool and must not be recycled while the side stream may still read them
+        out.update({"fused": fused, "weight_obj": weight, "view_status": tables[4], "tables": tables, "join": join_now})
         if join:
             join_now()
             out["join"] = _no_join
@@ -745,6 +767,7 @@ class FusionEngine:
         if key not in self._side:
             # high priority: the object branch ends in a chain of small kernels that should not queue behind filter CTAs
             self._side[key] = torch.cuda.Stream(device=device, priority=int(os.environ.get("DC_SIDE_PRIORITY", "-1")))
+            self._events[key] = (torch.cuda.Event(), torch.cuda.Event())
         return self._side[key]
 
     # ------------------------------------------------------------------ pixel-level path

@@ -420,6 +420,32 @@ def test_seg_histogram_ring_kernel(V, HW, nb, monkeypatch):
         assert int(out["ring"][1][v, 0]) + int(out["ring"][1][v, 1]) == n_out
 
 
+def test_two_stream_step_with_ring_kernel_equals_one_stream():
+    """A batch large enough (> 4 MB of int64 maps per SM) for dc_seg_histogram to take the ring kernel on its own: the
+    two-stream step (ring kernel and visibility filter sharing the SMs) against the one-stream step, bit for bit."""
+    from dropclip_b200.engine import FusionEngine, batch_from_device
+    from dropclip_b200.scenes import make_scene
+    eng = FusionEngine("cuda:0")
+    uniq = [make_scene(500 + i, n_views=26, n_points=20_000, n_objects=9, device="cuda:0", as_torch=True) for i in range(3)]
+    b = batch_from_device([uniq[i % 3] for i in range(10)], torch.device("cuda:0"), seg_dtype=torch.int64)
+    assert b.segs.numel() * 8 >= 148 * (4 << 20)
+    ref = None
+    try:
+        for overlap in (False, True, True):
+            eng.overlap = overlap
+            res = eng.fuse_object_level(b, 0.05, False, True, "max", torch.uint8, join=False)
+            comp = eng.compact_visibility(b, res["any_visible"], res["records"], res["rank"], torch.uint8)
+            res["join"]()
+            torch.cuda.synchronize()
+            cur = [res[k].clone() for k in ("fused", "weight_obj", "view_status", "any_visible")] + [comp[4].clone(), comp[1].clone()]
+            if ref is None:
+                ref = cur
+            for a, c in zip(ref, cur):
+                assert torch.equal(a.nan_to_num(), c.nan_to_num()) if a.is_floating_point() else torch.equal(a, c)
+    finally:
+        eng.overlap = True
+
+
 def test_two_stream_step_equals_one_stream():
     """fuse_object_level with the object branch on the side stream (ring histogram kernel beside the visibility filter)
     returns bit-identical results to the one-stream sequence, also when the join is deferred behind the compaction."""

@@ -41,6 +41,10 @@ def test_library_targets_sm100a_with_tensor_core_and_tma_instructions():
     assert "sm_100a" in sass
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, mnemonic
+    # the instance-histogram ring kernel of the two-stream step streams its input with 1-D bulk copies onto mbarriers
+    ring = sass[sass.index("seg_histogram_ring_kernel"):]
+    ring = ring[:ring.index("Function :", 10)] if "Function :" in ring[10:] else ring
+    assert "UBLKCP.S.G" in ring and "SYNCS.ARRIVE.TRANS64" in ring and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in ring
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -213,7 +217,8 @@ def test_host_staging_helpers_copy_and_narrow():
     assert lib.dc_host_gather_copy(None, 1, 4, None, 1) != 0  # null pointers are rejected, not dereferenced
 
 
-@pytest.mark.parametrize("name", ["r01_bench_final.json", "r02_bench_final.json", "r02_bench_n2.json", "r02_bench_n4.json"])
+@pytest.mark.parametrize("name", ["r01_bench_final.json", "r02_bench_final.json", "r02_bench_one_stream.json", "r02_bench_n2.json",
+                                  "r02_bench_n4.json"])
 def test_committed_bench_line_has_the_contract_keys(name):
     """profiles/rNN_bench_*.json are lines printed by bench.py on B200s; their shape is the driver's contract."""
     import json
@@ -236,6 +241,9 @@ def test_committed_bench_line_has_the_contract_keys(name):
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] in ("port", "reference")
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
     assert d["gpu_launches"] > 0 and {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    if "one_stream" in r:  # two-stream step: the dominant kernel's live window lies inside the step, the step's bytes below the peak
+        assert r["kernel"] == "seg_histogram" and r["kernels"]["seg_histogram"]["ms"] < d["ms_per_step"]
+        assert 0 < r["whole_step"]["frac"] < 1 and r["one_stream"]["ms_per_step"] > d["ms_per_step"]
 
 
 def test_host_staging_pool_survives_fork():
