@@ -468,7 +468,9 @@ extern "C" int dc_seg_histogram(const void* seg, int seg_dtype, int64_t total_vi
     // Alone: 6.7 TB/s (3 slots: 7.2, 8 warps: 5.8); the two-stream step: 2.75-2.78 ms with 2 slots, 2.80-2.85 with 3.
     int carve = dc::stream_overlap() ? dc::kOverlapCarveoutPct : cudaSharedmemCarveoutDefault;
     if (const char* e = getenv("DC_CARVEOUT_PCT")) carve = atoi(e);
-    const int flags = getenv("DC_SEG_FLAGS") ? atoi(getenv("DC_SEG_FLAGS")) : 0;
+    // measurement switches of benchmarks/ring_probe.py (1: copy only - WRONG counts -, 2: no L2 policy, 4: spin-wait):
+    // honoured only together with DC_SEG_MODE=ring, never on the default path
+    const int flags = forced && getenv("DC_SEG_FLAGS") ? atoi(getenv("DC_SEG_FLAGS")) : 0;
     if (warps == 16) return launch_ring<16, 3>(seg, bytes_per_view, total_views, nbins, depth, flags, carve, counts, outside, st);
     if (warps == 8) return launch_ring<8, 4>(seg, bytes_per_view, total_views, nbins, depth, flags, carve, counts, outside, st);
     return launch_ring<12, 3>(seg, bytes_per_view, total_views, nbins, depth, flags, carve, counts, outside, st);
